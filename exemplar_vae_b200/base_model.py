@@ -1,0 +1,383 @@
+"""Host-side mirror of the reference's model base classes (same method names, signatures and
+state_dict keys) over the exvae_b200 CUDA kernels:
+
+    BaseModel   models/BaseModel.py:16-271
+    AbsModel    models/AbsModel.py:9-49       (1-level VAE)
+    BaseHModel  models/AbsHModel.py:9-106     (2-level VAE)
+
+B200-first differences that do not change results:
+  * the training set lives in HBM (``resident``) and exemplars are gathered on the device,
+    instead of a CPU gather + 78 MB host->device copy every step (BaseModel.py:247,267);
+  * ``log_p_z(sum=True)`` never materialises the [B,C] matrix: distance, mask, normaliser and
+    log-sum-exp are one kernel (``ops.prior_lse``), optionally over a range-sharded bank;
+  * random draws (eps, exemplar indices) come from a device-side counter-based generator and
+    can be injected (``rng_override``) so runs can be replayed against the oracle.
+"""
+from __future__ import annotations
+
+import math
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .distributions import log_bernoulli, log_logistic_256, log_normal_diag, log_normal_standard, pairwise_distance
+from .layers import NonLinear, he_init
+
+
+class DeviceRng:
+    """Philox4x32-10 stream (seed, call-site subsequence, device counter).  The counter lives in
+    device memory and is advanced by a kernel after every draw, so a captured CUDA graph draws
+    fresh numbers on every replay."""
+
+    SUB_BERNOULLI, SUB_EXEMPLAR, SUB_EPS = 1, 2, 3
+
+    def __init__(self, seed: int = 0):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._counter = None
+
+    def counter(self, device) -> torch.Tensor:
+        if self._counter is None or self._counter.device != torch.device(device):
+            self._counter = torch.zeros(1, dtype=torch.int64, device=device)
+        return self._counter
+
+    def bernoulli(self, p):
+        c = self.counter(p.device)
+        out = ops.rng_bernoulli(p, self.seed, c, self.SUB_BERNOULLI)
+        ops.rng_advance_(c, 1)
+        return out
+
+    def normal(self, shape, device, sub=0):
+        c = self.counter(device)
+        out = ops.rng_normal(tuple(shape), self.seed, c, self.SUB_EPS + sub, device)
+        ops.rng_advance_(c, 1)
+        return out
+
+    def randint(self, low, high, n, device):
+        c = self.counter(device)
+        out = ops.rng_randint(low, high, n, self.seed, c, self.SUB_EXEMPLAR, device)
+        ops.rng_advance_(c, 1)
+        return out
+
+
+class BaseModel(nn.Module, ABC):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.rng = DeviceRng(getattr(args, "seed", 0))
+        self.rng_override: Optional[dict] = None   # {'eps': [tensors...], 'exemplar_indices': tensor}
+        self.bank_group = None                      # torch.distributed group when the bank is range-sharded
+        self._resident_cache = {}
+
+        if self.args.prior == 'vampprior':
+            raise NotImplementedError("prior='vampprior' (per-component log-variance bank) is SURVEY §8f-4, not built yet")
+        if self.args.prior == 'exemplar_prior':
+            self.prior_log_variance = torch.nn.Parameter(torch.randn((1)))
+
+        if self.args.input_type == 'binary':
+            self.p_x_mean = NonLinear(self.args.hidden_size, np.prod(self.args.input_size), activation=nn.Sigmoid())
+        elif self.args.input_type in ('gray', 'continuous'):
+            self.p_x_mean = NonLinear(self.args.hidden_size, np.prod(self.args.input_size))
+            self.p_x_logvar = NonLinear(self.args.hidden_size, np.prod(self.args.input_size),
+                                        activation=nn.Hardtanh(min_val=-4.5, max_val=0))
+            self.decoder_logstd = torch.nn.Parameter(torch.tensor([0.], requires_grad=True))
+
+        self.create_model(args)
+        self.he_initializer()
+
+    def he_initializer(self):
+        """models/BaseModel.py:39-44"""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                he_init(m)
+
+    @abstractmethod
+    def create_model(self, args):
+        pass
+
+    @abstractmethod
+    def kl_loss(self, latent_stats, exemplars_embedding, dataset, cache, x_indices):
+        pass
+
+    # ------------------------------------------------------------------ data residency
+    def resident(self, dataset) -> torch.Tensor:
+        """Device-resident copy of ``dataset.tensors[0]`` ([T,P] fp32), uploaded once."""
+        src = dataset.tensors[0] if hasattr(dataset, "tensors") else dataset
+        dev = self.prior_device()
+        if src.is_cuda:
+            return src
+        key = (src.data_ptr(), tuple(src.shape))
+        hit = self._resident_cache.get(key)
+        if hit is None:
+            hit = src.to(dev, dtype=torch.float32).contiguous()
+            self._resident_cache = {key: hit}
+        return hit
+
+    def prior_device(self):
+        return next(self.parameters()).device
+
+    # ------------------------------------------------------------------ loss
+    def reconstruction_loss(self, x, x_mean, x_logvar):
+        """models/BaseModel.py:54-63"""
+        if self.args.input_type == 'binary':
+            return log_bernoulli(x, x_mean, dim=1)
+        elif self.args.input_type in ('gray', 'continuous'):
+            if self.args.use_logit is True:
+                return log_normal_diag(x, x_mean, x_logvar, dim=1)
+            return log_logistic_256(x, x_mean, x_logvar, dim=1)
+        raise Exception('Wrong input type!')
+
+    def calculate_loss(self, x, beta=1., average=False, exemplars_embedding=None, cache=None, dataset=None):
+        """models/BaseModel.py:65-77 — returns (loss, RE, KL): scalars if ``average`` else [B]."""
+        x, x_indices = x
+        x_mean, x_logvar, latent_stats = self.forward(x)
+        RE = self.reconstruction_loss(x.reshape(x_mean.shape), x_mean, x_logvar)
+        KL = self.kl_loss(latent_stats, exemplars_embedding, dataset, cache, x_indices)
+        if average:
+            out3 = ops.elbo_reduce(RE, KL, beta, True)
+            return out3[0], out3[1], out3[2]
+        return ops.elbo_reduce(RE, KL, beta, False), RE, KL
+
+    def _next_eps(self, shape, device, sub=0):
+        ro = self.rng_override
+        if ro is not None and ro.get('eps'):
+            eps = ro['eps'].pop(0)
+            assert tuple(eps.shape) == tuple(shape), (eps.shape, shape)
+            return eps.to(device)
+        return self.rng.normal(shape, device, sub)
+
+    def reparameterize(self, mu, logvar, eps=None, sub=0):
+        """models/BaseModel.py:79-82 (eps ~ N(0,1) drawn on the device unless injected)."""
+        if eps is None:
+            eps = self._next_eps(mu.shape, mu.device, sub)
+        return ops.reparameterize(mu, logvar.expand_as(mu), eps)
+
+    # ------------------------------------------------------------------ exemplar prior
+    def log_p_z_exemplar(self, z, z_indices, exemplars_embedding, test):
+        """models/BaseModel.py:98-109 — the [B,C] matrix (materialising, no autograd)."""
+        centers, center_log_variance, center_indices = exemplars_embedding
+        lv = center_log_variance[0, :] if center_log_variance.dim() == 2 else center_log_variance
+        masked = (test is False) and (self.args.no_mask is False)
+        return ops.prior_logprob_matrix(z, centers, lv, z_indices if masked else None,
+                                        center_indices if masked else None)
+
+    def log_p_z(self, z, exemplars_embedding, sum=True, test=None):
+        """models/BaseModel.py:111-128"""
+        z, z_indices = z
+        if test is None:
+            test = not self.training
+        if self.args.prior == 'standard':
+            return log_normal_standard(z, dim=1)
+        elif self.args.prior == 'exemplar_prior':
+            if not sum:
+                return self.log_p_z_exemplar(z, z_indices, exemplars_embedding, test)
+            centers, center_log_variance, center_indices = exemplars_embedding
+            lv = center_log_variance[0, :] if center_log_variance.dim() == 2 else center_log_variance
+            masked = (test is False) and (self.args.no_mask is False) and z_indices is not None
+            c_total = getattr(exemplars_embedding, "c_total", None)
+            return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None,
+                                 c_total=c_total, group=self.bank_group if c_total is not None else None)
+        raise Exception('Wrong name of the prior!')
+
+    # ------------------------------------------------------------------ generation helpers
+    def generate_z(self, N=25, dataset=None):
+        """models/BaseModel.py:152-166"""
+        dev = self.prior_device()
+        if self.args.prior == 'standard':
+            return self.rng.normal((N, self.args.z1_size), dev)
+        rand_indices = self.rng.randint(0, self.args.training_set_size, N, dev)
+        exemplars = ops.gather_rows(self.resident(dataset), rand_indices)
+        mean, logvar = self.q_z(exemplars, prior=True)
+        return self.reparameterize(mean, logvar)
+
+    def reference_based_generation_z(self, N=25, reference_image=None):
+        """models/BaseModel.py:168-174"""
+        pseudo, log_var = self.q_z(reference_image.to(self.prior_device()), prior=True)
+        pseudo = pseudo.unsqueeze(1).expand(-1, N, -1).reshape(-1, pseudo.shape[-1])
+        log_var = log_var[0].unsqueeze(0).expand(len(pseudo), -1)
+        z = self.reparameterize(pseudo, log_var)
+        return z.reshape(-1, N, pseudo.shape[1])
+
+    def reconstruct_x(self, x):
+        x_reconstructed, _, _ = self.forward(x)
+        return x_reconstructed
+
+    def generate_x(self, N=25, dataset=None):
+        return self.generate_x_from_z(self.generate_z(N=N, dataset=dataset))
+
+    def reference_based_generation_x(self, N=25, reference_image=None):
+        z = self.reference_based_generation_z(N=N, reference_image=reference_image)
+        return self.generate_x_from_z(z.reshape(-1, z.shape[-1]))
+
+    def logit_inverse(self, x):
+        lambd = self.args.lambd
+        return (torch.sigmoid(x) - lambd) / (1 - 2 * lambd)
+
+    # ------------------------------------------------------------------ encoder over a bank
+    def q_z(self, x, prior=False):
+        """models/BaseModel.py:205-221 — returns (mean [R,D], logvar [R,D]).  With ``prior=True``
+        under the exemplar prior the log-variance is the learned scalar broadcast (a stride-0
+        view, no [R,D] tensor is written)."""
+        if 'conv' in self.args.model_name:
+            x = x.view(-1, self.args.input_size[0], self.args.input_size[1], self.args.input_size[2])
+        h = self.q_z_layers(x)
+        if self.args.model_name == 'convhvae_2level':
+            h = h.view(x.size(0), -1)
+        z_q_mean = self.q_z_mean(h)
+        if prior is True and self.args.prior == 'exemplar_prior':
+            z_q_logvar = self.prior_log_variance.expand(x.shape[0], self.args.z1_size)
+        else:
+            z_q_logvar = self.q_z_logvar(h)
+        return z_q_mean.reshape(-1, self.args.z1_size), z_q_logvar.reshape(-1, self.args.z1_size)
+
+    def cache_z(self, dataset, prior=True, cuda=True):
+        """models/BaseModel.py:223-241 — embed the whole (resident) dataset in chunks of 10 000."""
+        data = self.resident(dataset)
+        cached_z, cached_log_var = [], []
+        step = 10000
+        for i in range(math.ceil(data.shape[0] / step)):
+            m, lv = self.q_z(data[i * step:(i + 1) * step], prior=prior)
+            cached_z.append(m)
+            cached_log_var.append(lv)
+        return torch.cat(cached_z, dim=0), torch.cat(cached_log_var, dim=0)
+
+    def _exemplar_indices(self, device):
+        ro = self.rng_override
+        if ro is not None and ro.get('exemplar_indices') is not None:
+            return ro['exemplar_indices'].to(device).reshape(-1)
+        return self.rng.randint(0, self.args.training_set_size, self.args.number_components, device)
+
+    def get_exemplar_set(self, z_mean, z_log_var, dataset, cache, x_indices):
+        """models/BaseModel.py:243-254"""
+        if self.args.approximate_prior is False:
+            dev = z_mean.device
+            exemplars_indices = self._exemplar_indices(dev)
+            exemplars = ops.gather_rows(self.resident(dataset), exemplars_indices)
+            exemplars_z, log_variance = self.q_z(exemplars, prior=True)
+            return (exemplars_z, log_variance, exemplars_indices)
+        return self.get_approximate_nearest_exemplars(z=(z_mean, z_log_var, x_indices), dataset=dataset, cache=cache)
+
+    def get_approximate_nearest_exemplars(self, z, cache, dataset):
+        """models/BaseModel.py:256-271 — kNN exemplar selection against the cached bank.
+        Cache rows are refreshed in place (no autograd through the cache: the reference detaches
+        it after every step, utils/training.py:45-46, and only the re-encoded exemplars carry
+        gradient)."""
+        z, _, indices = z
+        dev = z.device
+        exemplars_indices = self._exemplar_indices(dev)
+        cached_z, cached_log_variance = cache
+        ops.scatter_rows_(cached_z, indices.reshape(-1), z.detach())
+        sub_cache = ops.gather_rows(cached_z, exemplars_indices)
+        nearest_indices, _ = ops.knn_topk(z.detach(), sub_cache, int(self.args.approximate_k))
+        uniq, count = ops.unique_positions(nearest_indices, sub_cache.shape[0])
+        nearest = uniq[:int(count.item())]            # data-dependent size: one host sync, like torch.unique
+        exemplars_indices = exemplars_indices[nearest].view(-1)
+        exemplars = ops.gather_rows(self.resident(dataset), exemplars_indices)
+        exemplars_z, log_variance = self.q_z(exemplars, prior=True)
+        ops.scatter_rows_(cached_z, exemplars_indices, exemplars_z.detach())
+        return (exemplars_z, log_variance, exemplars_indices)
+
+
+class AbsModel(BaseModel):
+    """models/AbsModel.py:9-49"""
+
+    def kl_loss(self, latent_stats, exemplars_embedding, dataset, cache, x_indices):
+        z_q, z_q_mean, z_q_logvar = latent_stats
+        if exemplars_embedding is None and self.args.prior == 'exemplar_prior':
+            exemplars_embedding = self.get_exemplar_set(z_q_mean, z_q_logvar, dataset, cache, x_indices)
+        log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+        log_q_z = log_normal_diag(z_q, z_q_mean, z_q_logvar, dim=1)
+        return ops.lincomb((-1.0, 1.0), log_p_z, log_q_z)     # -(log_p_z - log_q_z)
+
+    def generate_x_from_z(self, z, with_reparameterize=True):
+        generated_x, _ = self.p_x(z)
+        if getattr(self.args, "use_logit", False) is True:
+            return self.logit_inverse(generated_x)
+        return generated_x
+
+    def p_x(self, z):
+        if 'conv' in self.args.model_name:
+            z = z.reshape(-1, self.bottleneck, self.args.input_size[1] // 4, self.args.input_size[1] // 4)
+        z = self.p_x_layers(z)
+        x_mean = self.p_x_mean(z)
+        P = int(np.prod(self.args.input_size))
+        if self.args.input_type == 'binary':
+            x_logvar = torch.zeros(1, P, device=x_mean.device)
+        else:
+            if self.args.use_logit is False:
+                x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
+            x_logvar = self.decoder_logstd * x_mean.new_ones(size=x_mean.shape)
+        return x_mean.reshape(-1, P), x_logvar.reshape(-1, P)
+
+    def forward(self, x, label=0, num_categories=10):
+        z_q_mean, z_q_logvar = self.q_z(x)
+        z_q = self.reparameterize(z_q_mean, z_q_logvar)
+        x_mean, x_logvar = self.p_x(z_q)
+        return x_mean, x_logvar, (z_q, z_q_mean, z_q_logvar)
+
+
+class BaseHModel(BaseModel):
+    """models/AbsHModel.py:9-106"""
+
+    def kl_loss(self, latent_stats, exemplars_embedding, dataset, cache, x_indices):
+        z1_q, z1_q_mean, z1_q_logvar, z2_q, z2_q_mean, z2_q_logvar, z1_p_mean, z1_p_logvar = latent_stats
+        if exemplars_embedding is None and self.args.prior == 'exemplar_prior':
+            exemplars_embedding = self.get_exemplar_set(z2_q_mean, z2_q_logvar, dataset, cache, x_indices)
+        D1, D2 = self.args.z1_size, self.args.z2_size
+        log_p_z1 = log_normal_diag(z1_q.view(-1, D1), z1_p_mean.view(-1, D1), z1_p_logvar.view(-1, D1), dim=1)
+        log_q_z1 = log_normal_diag(z1_q.view(-1, D1), z1_q_mean.view(-1, D1), z1_q_logvar.view(-1, D1), dim=1)
+        log_p_z2 = self.log_p_z(z=(z2_q, x_indices), exemplars_embedding=exemplars_embedding)
+        log_q_z2 = log_normal_diag(z2_q.view(-1, D2), z2_q_mean.view(-1, D2), z2_q_logvar.view(-1, D2), dim=1)
+        return ops.lincomb((-1.0, -1.0, 1.0, 1.0), log_p_z1, log_p_z2, log_q_z1, log_q_z2)
+
+    def generate_x_from_z(self, z, with_reparameterize=True):
+        z1_mean, z1_logvar = self.p_z1(z)
+        z1 = self.reparameterize(z1_mean, z1_logvar) if with_reparameterize else z1_mean
+        generated_xs, _ = self.p_x(z1.view(-1, self.args.z1_size), z.view(-1, self.args.z2_size))
+        return generated_xs
+
+    def p_z1(self, z2):
+        z2 = self.p_z1_layers_z2(z2)
+        return self.p_z1_mean(z2), self.p_z1_logvar(z2)
+
+    def q_z1(self, x, z2):
+        x = self.q_z1_layers_x(x)
+        if self.args.model_name == 'convhvae_2level':
+            x = x.view(x.size(0), -1)
+        z2 = self.q_z1_layers_z2(z2)
+        h = torch.cat((x, z2), 1)
+        h = self.q_z1_layers_joint(h)
+        return self.q_z1_mean(h), self.q_z1_logvar(h)
+
+    def p_x(self, z1, z2, x=None):
+        z1 = self.p_x_layers_z1(z1)
+        z2 = self.p_x_layers_z2(z2)
+        h = torch.cat((z1, z2), 1)
+        if 'convhvae_2level' in self.args.model_name:
+            h = self.p_x_layers_joint_pre(h)
+            h = h.view(-1, self.args.input_size[0], self.args.input_size[1], self.args.input_size[2])
+        h_decoder = self.p_x_layers_joint(h)
+        x_mean = self.p_x_mean(h_decoder)
+        P = int(np.prod(self.args.input_size))
+        if 'convhvae_2level' in self.args.model_name:
+            x_mean = x_mean.view(-1, P)
+        if self.args.input_type == 'binary':
+            x_logvar = torch.zeros(1, P, device=x_mean.device)
+        else:
+            x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
+            x_logvar = self.p_x_logvar(h_decoder)
+            if 'convhvae_2level' in self.args.model_name:
+                x_logvar = x_logvar.view(-1, P)
+        return x_mean, x_logvar
+
+    def forward(self, x):
+        z2_q_mean, z2_q_logvar = self.q_z(x)
+        z2_q = self.reparameterize(z2_q_mean, z2_q_logvar, sub=0)
+        z1_q_mean, z1_q_logvar = self.q_z1(x, z2_q)
+        z1_q = self.reparameterize(z1_q_mean, z1_q_logvar, sub=1)
+        z1_p_mean, z1_p_logvar = self.p_z1(z2_q)
+        x_mean, x_logvar = self.p_x(z1_q, z2_q)
+        return x_mean, x_logvar, (z1_q, z1_q_mean, z1_q_logvar, z2_q, z2_q_mean, z2_q_logvar, z1_p_mean, z1_p_logvar)

@@ -1,0 +1,473 @@
+// K3 — dense layers of the encoder/decoder (sm_100a), fp32 FMA-pipe GEMM with fused epilogues.
+//
+//   GatedDense  utils/nn.py:44-69    out = (x Wh^T + bh) * sigmoid(x Wg^T + bg)
+//   NonLinear / nn.Linear  utils/nn.py:29-41   out = act(x W^T + b), act in {none, sigmoid, hardtanh}
+// and their backward passes (dx, dW, db).
+//
+// One kernel template covers the four operand layouts the forward/backward need:
+//   A "KC": A[m][k] with k contiguous (activations, gradients)      A "XC": A[k][m] with m contiguous (dY^T)
+//   B "KC": B[n][k] with k contiguous (nn.Linear weights, forward)  B "XC": B[k][n] with n contiguous (W for dx, x for dW)
+// Operand B (and XC-A) may be split in two segments so the h- and g-branch weights of a gated
+// layer are read in place (the reference keeps them as two nn.Linear modules, and the
+// state_dict key names must survive).  In the gated forward a 128-wide tile holds 64 h-columns
+// and the 64 matching g-columns, so h*sigmoid(g) is formed in registers.
+//
+// CTA tile 128x128x16, 256 threads, 8x8 outputs per thread (two 4x4 quadrant pairs), smem
+// double buffering with register prefetch: one __syncthreads per k-step.
+// Precision: fp32 operands and accumulation (the 1e-4 ELBO parity bar rules out single-pass
+// tf32/bf16 tensor-core operands; a 3xTF32 tcgen05 path is the planned upgrade).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace exvae {
+namespace {
+
+constexpr int GM = 128, GN = 128, GK = 16, GP = GM + 4;
+enum { L_KC = 0, L_XC = 1 };
+enum { EPI_BIAS_ACT = 0, EPI_GATED = 1, EPI_PLAIN = 2, EPI_SPLITK = 3 };
+
+struct GemmP {
+  const float* A;
+  int lda;
+  const float* B0;
+  const float* B1;
+  int ldb;
+  int bseg;  // XC-B: rows k >= bseg come from B1.  KC-B (non gated): unused
+  int M, N, K;
+  int kchunk;  // split-K: blockIdx.z covers [z*kchunk, min(K,(z+1)*kchunk))
+  const float* bias0;
+  const float* bias1;
+  float* out0;
+  float* out1;
+  float* out2;
+  int ldc;
+  int act;
+  float lo, hi;
+  int O;       // gated forward: number of output columns
+  int a_vec;   // A rows are 16-byte aligned and lda % 4 == 0
+  int b_vec;
+  int c_vec;   // output rows are 16-byte aligned and ldc % 4 == 0
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// load 4 consecutive elements starting at p[i0], valid while index < limit
+__device__ __forceinline__ float4 load4(const float* __restrict__ p, int i0, int limit, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p == nullptr) return v;
+  if (vec && i0 + 3 < limit) return *reinterpret_cast<const float4*>(p + i0);
+  if (i0 < limit) v.x = p[i0];
+  if (i0 + 1 < limit) v.y = p[i0 + 1];
+  if (i0 + 2 < limit) v.z = p[i0 + 2];
+  if (i0 + 3 < limit) v.w = p[i0 + 3];
+  return v;
+}
+
+template <int AL, int BL, int EPI>
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmP p) {
+  __shared__ __align__(16) float As[2][GK][GP];
+  __shared__ __align__(16) float Bs[2][GK][GP];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM;
+  const int n0 = (EPI == EPI_GATED) ? blockIdx.x * (GN / 2) : blockIdx.x * GN;
+  const int kbeg = blockIdx.z * p.kchunk;
+  const int kend = min(p.K, kbeg + p.kchunk);
+
+  // per-thread load coordinates
+  const int kc_r = tid >> 2, kc_k = (tid & 3) * 4;   // KC: rows kc_r, kc_r+64 ; k offset kc_k
+  const int xc_k = tid >> 5, xc_x = (tid & 31) * 4;  // XC: k rows xc_k, xc_k+8 ; x offset xc_x
+
+  const float* a_row[2] = {nullptr, nullptr};
+  if (AL == L_KC) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m0 + kc_r + 64 * h;
+      a_row[h] = m < p.M ? p.A + (size_t)m * p.lda : nullptr;
+    }
+  }
+  const float* b_row[2] = {nullptr, nullptr};
+  if (BL == L_KC) {
+    if (EPI == EPI_GATED) {
+      const int j = n0 + kc_r;
+      b_row[0] = j < p.O ? p.B0 + (size_t)j * p.ldb : nullptr;
+      b_row[1] = j < p.O ? p.B1 + (size_t)j * p.ldb : nullptr;
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = n0 + kc_r + 64 * h;
+        b_row[h] = n < p.N ? p.B0 + (size_t)n * p.ldb : nullptr;
+      }
+    }
+  }
+
+  float4 ra[2], rb[2];
+  auto fetch = [&](int k0) {
+    if (AL == L_KC) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) ra[h] = load4(a_row[h], k0 + kc_k, kend, p.a_vec);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + xc_k + 8 * h;
+        ra[h] = load4(k < kend ? p.A + (size_t)k * p.lda : nullptr, m0 + xc_x, p.M, p.a_vec);
+      }
+    }
+    if (BL == L_KC) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) rb[h] = load4(b_row[h], k0 + kc_k, kend, p.b_vec);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + xc_k + 8 * h;
+        const float* row = nullptr;
+        if (k < kend) row = k < p.bseg ? p.B0 + (size_t)k * p.ldb : p.B1 + (size_t)(k - p.bseg) * p.ldb;
+        rb[h] = load4(row, n0 + xc_x, p.N, p.b_vec);
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+    if (AL == L_KC) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = kc_r + 64 * h;
+        As[buf][kc_k + 0][r] = ra[h].x;
+        As[buf][kc_k + 1][r] = ra[h].y;
+        As[buf][kc_k + 2][r] = ra[h].z;
+        As[buf][kc_k + 3][r] = ra[h].w;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) *reinterpret_cast<float4*>(&As[buf][xc_k + 8 * h][xc_x]) = ra[h];
+    }
+    if (BL == L_KC) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = kc_r + 64 * h;
+        Bs[buf][kc_k + 0][r] = rb[h].x;
+        Bs[buf][kc_k + 1][r] = rb[h].y;
+        Bs[buf][kc_k + 2][r] = rb[h].z;
+        Bs[buf][kc_k + 3][r] = rb[h].w;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) *reinterpret_cast<float4*>(&Bs[buf][xc_k + 8 * h][xc_x]) = rb[h];
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = (kend > kbeg) ? (kend - kbeg + GK - 1) / GK : 0;
+  if (nk > 0) {
+    fetch(kbeg);
+    stash(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch(kbeg + (kt + 1) * GK);
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= p.M) continue;
+    if (EPI == EPI_GATED) {
+      const int j0 = n0 + tx * 4;
+      float o[4], hh[4], ss[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = j0 + j;
+        const float bh = (col < p.O && p.bias0) ? p.bias0[col] : 0.f;
+        const float bg = (col < p.O && p.bias1) ? p.bias1[col] : 0.f;
+        hh[j] = acc[i][j] + bh;
+        ss[j] = sigmoidf_(acc[i][4 + j] + bg);
+        o[j] = hh[j] * ss[j];
+      }
+      const size_t base = (size_t)m * p.ldc + j0;
+      if (j0 + 3 < p.O && p.c_vec) {
+        *reinterpret_cast<float4*>(p.out0 + base) = make_float4(o[0], o[1], o[2], o[3]);
+        if (p.out1) *reinterpret_cast<float4*>(p.out1 + base) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        if (p.out2) *reinterpret_cast<float4*>(p.out2 + base) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j0 + j < p.O) {
+            p.out0[base + j] = o[j];
+            if (p.out1) p.out1[base + j] = hh[j];
+            if (p.out2) p.out2[base + j] = ss[j];
+          }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c0 = n0 + 64 * q + tx * 4;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = acc[i][4 * q + j];
+          if (EPI == EPI_BIAS_ACT) {
+            const int col = c0 + j;
+            if (p.bias0 && col < p.N) v += p.bias0[col];
+            if (p.act == EXVAE_ACT_SIGMOID) v = sigmoidf_(v);
+            else if (p.act == EXVAE_ACT_HARDTANH) v = fminf(fmaxf(v, p.lo), p.hi);
+            else if (p.act == EXVAE_ACT_RELU) v = fmaxf(v, 0.f);
+          }
+          o[j] = v;
+        }
+        float* dst = (EPI == EPI_SPLITK) ? p.out0 + ((size_t)blockIdx.z * p.M + m) * p.ldc : p.out0 + (size_t)m * p.ldc;
+        if (c0 + 3 < p.N && p.c_vec) {
+          *reinterpret_cast<float4*>(dst + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c0 + j < p.N) dst[c0 + j] = o[j];
+        }
+      }
+    }
+  }
+}
+
+// out rows m < mseg -> out0[m], else out1[m - mseg]
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S, int M, int N, int mseg,
+                                                            float* __restrict__ out0, float* __restrict__ out1) {
+  const size_t total = (size_t)M * N;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += part[(size_t)s * total + e];
+    const int m = (int)(e / N);
+    if (m < mseg) out0[e] = a;
+    else out1[e - (size_t)mseg * N] = a;
+  }
+}
+
+// stage 1 of the column sum (bias gradients): block = 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ src, int R, int ncols, int rows_per,
+                                                             float* __restrict__ part) {
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float a = 0.f;
+  if (col < ncols)
+    for (int r = r0 + ry; r < r1; r += 8) a += src[(size_t)r * ncols + col];
+  sh[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && col < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][cx];
+    part[(size_t)blockIdx.y * ncols + col] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int S, int ncols, int seg,
+                                                           float* __restrict__ out0, float* __restrict__ out1) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += part[(size_t)s * ncols + col];
+  if (col < seg) {
+    if (out0) out0[col] = a;
+  } else if (out1) {
+    out1[col - seg] = a;
+  }
+}
+
+// dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*h*sig*(1-sig)      (d/dh and d/dg of h*sigmoid(g))
+__global__ void __launch_bounds__(256) gated_dpre_kernel(const float* __restrict__ dout, const float* __restrict__ h,
+                                                         const float* __restrict__ sig, long long R, int O,
+                                                         float* __restrict__ dcat) {
+  const long long total = R * O;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / O;
+    const int j = (int)(e - r * O);
+    const float d = dout[e], s = sig[e], hv = h[e];
+    dcat[r * 2 * O + j] = d * s;
+    dcat[r * 2 * O + O + j] = d * hv * s * (1.f - s);
+  }
+}
+// dpre = dout * act'(out)
+__global__ void __launch_bounds__(256) act_dpre_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                       long long n, int act, float lo, float hi,
+                                                       float* __restrict__ dpre) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float o = out[e];
+    float d = dout[e];
+    if (act == EXVAE_ACT_SIGMOID) d *= o * (1.f - o);
+    else if (act == EXVAE_ACT_HARDTANH) d = (o > lo && o < hi) ? d : 0.f;
+    else if (act == EXVAE_ACT_RELU) d = o > 0.f ? d : 0.f;
+    dpre[e] = d;
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int ew_blocks(long long n) { return (int)std::min<long long>((n + 255) / 256, 148LL * 16); }
+
+template <int AL, int BL, int EPI>
+int launch_gemm(const GemmP& p, int splits, cudaStream_t st) {
+  dim3 grid(EPI == EPI_GATED ? ceil_div(p.O, GN / 2) : ceil_div(p.N, GN), ceil_div(p.M, GM), splits);
+  sgemm_kernel<AL, BL, EPI><<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EXVAE_OK : (int)e;
+}
+
+struct BwdPlan {
+  int S, kchunk, S2, rows_per;
+  size_t off_dcat, off_part, off_cs, bytes;
+};
+// ncat = number of pre-activation columns (2*O gated, O linear); need_dcat: a dpre buffer is needed
+inline BwdPlan bwd_plan(int R, int K, int ncat, bool need_dcat) {
+  BwdPlan b;
+  const int tiles = ceil_div(ncat, GM) * ceil_div(K, GN);
+  int S = ceil_div(2 * sm_count(), tiles);
+  S = std::max(1, std::min(S, ceil_div(R, 4 * GK)));
+  b.kchunk = ceil_div(ceil_div(R, S), GK) * GK;
+  b.S = ceil_div(R, b.kchunk);
+  b.S2 = std::max(1, std::min(64, ceil_div(R, 256)));
+  b.rows_per = ceil_div(R, b.S2);
+  size_t off = 0;
+  b.off_dcat = off;
+  if (need_dcat) off += align_up(sizeof(float) * (size_t)R * ncat, 256);
+  b.off_part = off;
+  off += align_up(sizeof(float) * (size_t)b.S * ncat * K, 256);
+  b.off_cs = off;
+  off += align_up(sizeof(float) * (size_t)b.S2 * ncat, 256);
+  b.bytes = off;
+  return b;
+}
+
+// shared tail of both backward passes: dx, dW (split-K over rows + reduce), db
+int dense_bwd_common(const float* x, const float* W0, const float* W1, const float* dcat, int R, int K, int ncat, int oseg,
+                     float* dx, float* dW0, float* dW1, float* db0, float* db1, const BwdPlan& plan, char* ws,
+                     cudaStream_t st) {
+  int rc;
+  if (dx) {  // dx[R,K] = dcat[R,ncat] . Wcat[ncat,K]
+    GemmP p{};
+    p.A = dcat; p.lda = ncat; p.B0 = W0; p.B1 = W1 ? W1 : W0; p.ldb = K; p.bseg = W1 ? oseg : ncat;
+    p.M = R; p.N = K; p.K = ncat; p.kchunk = ncat; p.out0 = dx; p.ldc = K;
+    p.c_vec = (K % 4 == 0) && al16(dx);
+    p.a_vec = (ncat % 4 == 0) && al16(dcat);
+    p.b_vec = (K % 4 == 0) && al16(W0) && (!W1 || al16(W1));
+    rc = launch_gemm<L_KC, L_XC, EPI_PLAIN>(p, 1, st);
+    if (rc) return rc;
+  }
+  {  // dWcat[ncat,K] = dcat^T[ncat,R] . x[R,K]   (reduction over the R rows, split across CTAs)
+    float* part = reinterpret_cast<float*>(ws + plan.off_part);
+    GemmP p{};
+    p.A = dcat; p.lda = ncat; p.B0 = x; p.B1 = x; p.ldb = K; p.bseg = R;
+    p.M = ncat; p.N = K; p.K = R; p.kchunk = plan.kchunk; p.out0 = part; p.ldc = K;
+    p.c_vec = (K % 4 == 0) && (((size_t)ncat * K) % 4 == 0) && al16(part);
+    p.a_vec = (ncat % 4 == 0) && al16(dcat);
+    p.b_vec = (K % 4 == 0) && al16(x);
+    rc = launch_gemm<L_XC, L_XC, EPI_SPLITK>(p, plan.S, st);
+    if (rc) return rc;
+    splitk_reduce_kernel<<<ew_blocks((long long)ncat * K), 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0,
+                                                                         dW1 ? dW1 : dW0);
+    EXVAE_CUDA(cudaGetLastError());
+  }
+  if (db0 || db1) {
+    float* cs = reinterpret_cast<float*>(ws + plan.off_cs);
+    dim3 g1(ceil_div(ncat, 32), plan.S2);
+    colsum_partial_kernel<<<g1, 256, 0, st>>>(dcat, R, ncat, plan.rows_per, cs);
+    EXVAE_CUDA(cudaGetLastError());
+    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1);
+    EXVAE_CUDA(cudaGetLastError());
+  }
+  return EXVAE_OK;
+}
+
+}  // namespace
+}  // namespace exvae
+
+using namespace exvae;
+
+extern "C" int exvae_gated_dense_fwd(const float* x, const float* Wh, const float* bh, const float* Wg, const float* bg,
+                                     int R, int K, int O, float* out, float* h_lin, float* sig,
+                                     exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(x && Wh && Wg && out && R > 0 && K > 0 && O > 0);
+  GemmP p{};
+  p.A = x; p.lda = K; p.B0 = Wh; p.B1 = Wg; p.ldb = K; p.M = R; p.N = 2 * O; p.K = K; p.kchunk = K;
+  p.bias0 = bh; p.bias1 = bg; p.out0 = out; p.out1 = h_lin; p.out2 = sig; p.ldc = O; p.O = O;
+  p.a_vec = (K % 4 == 0) && al16(x);
+  p.b_vec = (K % 4 == 0) && al16(Wh) && al16(Wg);
+  p.c_vec = (O % 4 == 0) && al16(out) && (!h_lin || al16(h_lin)) && (!sig || al16(sig));
+  return launch_gemm<L_KC, L_KC, EPI_GATED>(p, 1, as_stream(stream));
+}
+
+extern "C" size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O) {
+  if (R <= 0 || K <= 0 || O <= 0) return 0;
+  return bwd_plan(R, K, 2 * O, true).bytes;
+}
+
+extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin,
+                                     const float* sig, const float* dout, int R, int K, int O, float* dx, float* dWh,
+                                     float* dbh, float* dWg, float* dbg, void* ws, size_t ws_bytes,
+                                     exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(x && Wh && Wg && h_lin && sig && dout && dWh && dWg && ws && R > 0 && K > 0 && O > 0);
+  const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
+  if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char* w = static_cast<char*>(ws);
+  float* dcat = reinterpret_cast<float*>(w + plan.off_dcat);
+  gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, h_lin, sig, R, O, dcat);
+  EXVAE_CUDA(cudaGetLastError());
+  return dense_bwd_common(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, plan, w, st);
+}
+
+extern "C" int exvae_linear_fwd(const float* x, const float* W, const float* b, int R, int K, int O, int act, float lo,
+                                float hi, float* out, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(x && W && out && R > 0 && K > 0 && O > 0);
+  EXVAE_CHECK_ARG(act >= EXVAE_ACT_NONE && act <= EXVAE_ACT_RELU);
+  GemmP p{};
+  p.A = x; p.lda = K; p.B0 = W; p.B1 = W; p.ldb = K; p.M = R; p.N = O; p.K = K; p.kchunk = K;
+  p.bias0 = b; p.out0 = out; p.ldc = O; p.act = act; p.lo = lo; p.hi = hi;
+  p.a_vec = (K % 4 == 0) && al16(x);
+  p.b_vec = (K % 4 == 0) && al16(W);
+  p.c_vec = (O % 4 == 0) && al16(out);
+  return launch_gemm<L_KC, L_KC, EPI_BIAS_ACT>(p, 1, as_stream(stream));
+}
+
+extern "C" size_t exvae_linear_bwd_workspace_bytes(int R, int K, int O) {
+  if (R <= 0 || K <= 0 || O <= 0) return 0;
+  return bwd_plan(R, K, O, true).bytes;
+}
+
+extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out, const float* dout, int R, int K, int O,
+                                int act, float lo, float hi, float* dx, float* dW, float* db, void* ws, size_t ws_bytes,
+                                exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(x && W && dout && dW && ws && R > 0 && K > 0 && O > 0);
+  EXVAE_CHECK_ARG(act == EXVAE_ACT_NONE || out != nullptr);
+  const BwdPlan plan = bwd_plan(R, K, O, true);
+  if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char* w = static_cast<char*>(ws);
+  const float* dpre = dout;
+  if (act != EXVAE_ACT_NONE) {
+    float* buf = reinterpret_cast<float*>(w + plan.off_dcat);
+    act_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, out, (long long)R * O, act, lo, hi, buf);
+    EXVAE_CUDA(cudaGetLastError());
+    dpre = buf;
+  }
+  return dense_bwd_common(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, plan, w, st);
+}

@@ -1,0 +1,721 @@
+// K1 — fused exemplar-prior kernel (sm_100a).
+//
+// Replaces, in one pass and without materialising any [B,C] matrix:
+//   log_normal_diag_vectorized -> pairwise_distance   utils/distributions.py:12-25
+//   leave-one-out mask + normaliser                    models/BaseModel.py:98-109
+//   max-shifted log-sum-exp over exemplars             models/BaseModel.py:123-125
+// and its backward (dz, dmu, dlogvar) with flash-attention-style recomputation from the saved
+// row log-sum.
+//
+// Data layout in HBM (workspace, staged by prior_stage_kernel):
+//   zs [Bpad, LD]  rows z_b / sigma            ms [Cpad, LD]  rows mu_n / sigma   (zero padded)
+//   LD = 4 * (ceil(D/4) | 1): an ODD number of 16-byte chunks per row, so the float4 reads
+//   of 8 consecutive rows hit 8 distinct bank groups (no shared-memory conflicts) and a
+//   whole [tile_rows, LD] tile is one contiguous span -> ONE bulk-async (TMA engine) copy.
+//   nb2 [Cpad] = -0.5*||ms_n||^2 * log2(e)   (-inf in the padding => padded columns vanish)
+//   logit2[b,n] = log2(e) * (zs_b . ms_n) + nb2[n]      (row constants are added in finalize)
+//
+// D = 40 is not an MMA-friendly K and the 1e-4 parity bar excludes tf32/bf16 operands
+// (SURVEY.md §7), so the contraction runs on the fp32 FMA pipe with an 8x4 register tile per
+// thread; the tensor-core variant only pays for D >= 64 and is a later-round item.
+#include "common.cuh"
+
+namespace exvae {
+namespace {
+
+constexpr int PR_THREADS = 256;
+constexpr int PR_BM = 128;  // rows (z) per CTA tile
+constexpr int PR_BN = 64;   // columns (exemplars) per tile
+constexpr int PR_TM = 8;
+constexpr int PR_TN = 4;
+constexpr int64_t kPadIdx = INT64_MIN;
+
+struct PriorWs {
+  int LD, kch, Bpad, Cpad, nsplit, ntile;
+  float* zs;
+  float* hz;
+  float* ms;
+  float* nb2;
+  int64_t* cidx;
+  float* isig;
+  float* part;         // [Bpad, nsplit, 4]
+  float* dzs_part;     // [ntile, Bpad, LD]
+  float* rowsum_part;  // [ntile, Bpad]
+  float* coldot_part;  // [ntile, LD]
+  float* rowdot;       // [Bpad, LD]
+  float* rs;           // [Bpad]
+  size_t bytes;
+};
+
+inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
+  PriorWs w;
+  w.kch = ceil_div(D, 4);
+  w.LD = 4 * (w.kch | 1);
+  w.Bpad = ceil_div(B, PR_BM) * PR_BM;
+  w.Cpad = ceil_div(C, 128) * 128;
+  w.ntile = w.Cpad / PR_BN;
+  const int rb = w.Bpad / PR_BM;
+  int target = 2 * sm_count();
+  int ns = target / rb;
+  if (ns < 1) ns = 1;
+  if (ns > w.ntile) ns = w.ntile;
+  w.nsplit = ns;
+  size_t off = 0;
+  char* p = static_cast<char*>(base);
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  w.zs = (float*)take(sizeof(float) * (size_t)w.Bpad * w.LD);
+  w.hz = (float*)take(sizeof(float) * w.Bpad);
+  w.ms = (float*)take(sizeof(float) * (size_t)w.Cpad * w.LD);
+  w.nb2 = (float*)take(sizeof(float) * w.Cpad);
+  w.cidx = (int64_t*)take(sizeof(int64_t) * w.Cpad);
+  w.isig = (float*)take(sizeof(float) * w.LD);
+  w.part = (float*)take(sizeof(float) * 4 * (size_t)w.Bpad * w.nsplit);
+  if (need_bwd) {
+    w.dzs_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.Bpad * w.LD);
+    w.rowsum_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.Bpad);
+    w.coldot_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.LD);
+    w.rowdot = (float*)take(sizeof(float) * (size_t)w.Bpad * w.LD);
+    w.rs = (float*)take(sizeof(float) * w.Bpad);
+  } else {
+    w.dzs_part = w.rowsum_part = w.coldot_part = w.rowdot = w.rs = nullptr;
+  }
+  w.bytes = off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------- staging
+// One warp per row: x / sigma (IEEE division like utils/distributions.py:23), zero padding,
+// half squared norm.  Rows [0,Cpad) are the bank, rows [Cpad, Cpad+Bpad) are z.
+__global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restrict__ z, const float* __restrict__ mu,
+                                                          const float* __restrict__ logvar,
+                                                          const int64_t* __restrict__ mu_idx, int B, int C, int D,
+                                                          int LD, int Bpad, int Cpad, float* __restrict__ zs,
+                                                          float* __restrict__ hz, float* __restrict__ ms,
+                                                          float* __restrict__ nb2, int64_t* __restrict__ cidx,
+                                                          float* __restrict__ isig) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x < LD) {
+    const int d = threadIdx.x;
+    isig[d] = d < D ? 1.0f / expf(0.5f * logvar[d]) : 0.f;
+  }
+  if (row >= Cpad + Bpad) return;
+  const bool is_bank = row < Cpad;
+  const int r = is_bank ? row : row - Cpad;
+  const bool valid = is_bank ? (r < C) : (r < B);
+  const float* src = is_bank ? mu + (size_t)r * D : z + (size_t)r * D;
+  float* dst = is_bank ? ms + (size_t)r * LD : zs + (size_t)r * LD;
+  float ss = 0.f;
+  for (int d = lane; d < LD; d += 32) {
+    float v = 0.f;
+    if (valid && d < D) v = src[d] / expf(0.5f * logvar[d]);
+    dst[d] = v;
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    if (is_bank) {
+      nb2[r] = valid ? -0.5f * ss * kLog2e : -INFINITY;
+      cidx[r] = valid ? (mu_idx ? mu_idx[r] : (int64_t)-1) : kPadIdx;
+    } else {
+      hz[r] = 0.5f * ss;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- forward
+struct FwdSmem {
+  // offsets in bytes from the dynamic shared base (computed on host and device identically)
+  int zt, mt0, mt1, nb0, nb1, ci0, ci1, red, zi, bar, total;
+};
+__host__ __device__ inline FwdSmem fwd_smem_layout(int LD) {
+  FwdSmem s;
+  int off = 0;
+  s.zt = off;  off += PR_BM * LD * 4;
+  s.mt0 = off; off += PR_BN * LD * 4;
+  s.mt1 = off; off += PR_BN * LD * 4;
+  s.ci0 = off; off += PR_BN * 8;
+  s.ci1 = off; off += PR_BN * 8;
+  s.nb0 = off; off += PR_BN * 4;
+  s.nb1 = off; off += PR_BN * 4;
+  s.red = off; off += PR_BM * 2 * 4 * 4;  // [BM][2] x (m, s, cnt, pad)
+  s.zi = off;  off += PR_BM * 8;          // dataset index of each row (int64)
+  s.bar = off; off += 4 * 8;
+  s.total = off;
+  return s;
+}
+
+// 8x4 register tile: acc[i][j] = zs[row ty+16i] . ms[col tx+16j]
+__device__ __forceinline__ void tile_dot(const float4* __restrict__ zt4, const float4* __restrict__ mt4, int LD4,
+                                         int kch, int ty, int tx, float (&acc)[PR_TM][PR_TN]) {
+#pragma unroll
+  for (int i = 0; i < PR_TM; ++i)
+#pragma unroll
+    for (int j = 0; j < PR_TN; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < kch; ++k) {
+    float4 a[PR_TM];
+#pragma unroll
+    for (int i = 0; i < PR_TM; ++i) a[i] = zt4[(ty + 16 * i) * LD4 + k];
+#pragma unroll
+    for (int j = 0; j < PR_TN; ++j) {
+      const float4 b = mt4[(tx + 16 * j) * LD4 + k];
+#pragma unroll
+      for (int i = 0; i < PR_TM; ++i) {
+        acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
+        acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
+        acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
+        acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+      }
+    }
+  }
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(PR_THREADS, 2)
+    prior_lse_fwd_kernel(const float* __restrict__ zs, const float* __restrict__ ms, const float* __restrict__ nb2,
+                         const int64_t* __restrict__ cidx, const int64_t* __restrict__ z_idx, int B, int C, int LD,
+                         int kch, int ntile, int nsplit, float* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FwdSmem L = fwd_smem_layout(LD);
+  float* zt = reinterpret_cast<float*>(smem + L.zt);
+  // stage `buf` of the double-buffered bank tile lives at base + buf * stride (no pointer arrays)
+  float* const mt_base = reinterpret_cast<float*>(smem + L.mt0);
+  float* const nb_base = reinterpret_cast<float*>(smem + L.nb0);
+  long long* const ci_base = reinterpret_cast<long long*>(smem + L.ci0);
+  const int mt_stride = PR_BN * LD;
+  float4* red = reinterpret_cast<float4*>(smem + L.red);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);  // [0],[1]: bank stages, [2]: z tile
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = (lane & 7) + 8 * (warp & 1);
+  const int ty = (lane >> 3) + 4 * (warp >> 1);
+  const int split = blockIdx.x, rb = blockIdx.y;
+  const int t0 = (int)(((long long)ntile * split) / nsplit);
+  const int t1 = (int)(((long long)ntile * (split + 1)) / nsplit);
+  const int LD4 = LD >> 2;
+  const uint32_t tile_bytes = PR_BN * LD * 4;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue_tile = [&](int t, int buf) {
+    mbar_arrive_expect_tx(&bar[buf], tile_bytes + PR_BN * 4 + (MASK ? PR_BN * 8 : 0));
+    bulk_g2s(mt_base + buf * mt_stride, ms + (size_t)t * PR_BN * LD, tile_bytes, &bar[buf]);
+    bulk_g2s(nb_base + buf * PR_BN, nb2 + (size_t)t * PR_BN, PR_BN * 4, &bar[buf]);
+    if (MASK) bulk_g2s(ci_base + buf * PR_BN, cidx + (size_t)t * PR_BN, PR_BN * 8, &bar[buf]);
+  };
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar[2], PR_BM * LD * 4);
+    bulk_g2s(zt, zs + (size_t)rb * PR_BM * LD, PR_BM * LD * 4, &bar[2]);
+    if (t0 < t1) issue_tile(t0, 0);
+  }
+
+  // full 64-bit row indices stay in shared memory; registers keep the low words for the
+  // cheap pre-test (a hit is rare: a handful of pairs per row out of C)
+  long long* zis = reinterpret_cast<long long*>(smem + L.zi);
+  if (MASK && tid < PR_BM) {
+    const int b = rb * PR_BM + tid;
+    zis[tid] = b < B ? z_idx[b] : kPadIdx;
+  }
+  __syncthreads();
+  float m[PR_TM], s[PR_TM], cnt[PR_TM];
+  int zlo[PR_TM];
+#pragma unroll
+  for (int i = 0; i < PR_TM; ++i) {
+    m[i] = -INFINITY;
+    s[i] = 0.f;
+    cnt[i] = 0.f;
+    zlo[i] = MASK ? (int)zis[ty + 16 * i] : 0;
+  }
+  mbar_wait(&bar[2], 0);
+
+  const float4* zt4 = reinterpret_cast<const float4*>(zt);
+  for (int t = t0; t < t1; ++t) {
+    const int it = t - t0, buf = it & 1;
+    if (tid == 0 && t + 1 < t1) issue_tile(t + 1, buf ^ 1);
+    mbar_wait(&bar[buf], (it >> 1) & 1);
+
+    float acc[PR_TM][PR_TN];
+    tile_dot(zt4, reinterpret_cast<const float4*>(mt_base + buf * mt_stride), LD4, kch, ty, tx, acc);
+    const float* nbs_t = nb_base + buf * PR_BN;
+    const long long* cis_t = ci_base + buf * PR_BN;
+
+    float nbv[PR_TN];
+    int clo[PR_TN];
+#pragma unroll
+    for (int j = 0; j < PR_TN; ++j) {
+      nbv[j] = nbs_t[tx + 16 * j];
+      clo[j] = MASK ? (int)cis_t[tx + 16 * j] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < PR_TM; ++i) {
+      float u[PR_TN];
+#pragma unroll
+      for (int j = 0; j < PR_TN; ++j) {
+        u[j] = fmaf(acc[i][j], kLog2e, nbv[j]);
+        if (MASK) {
+          if (clo[j] == zlo[i]) {                          // cheap 32-bit pre-test, rare hit
+            const long long cfull = cis_t[tx + 16 * j];
+            if (cfull == zis[ty + 16 * i] && cfull != kPadIdx) {
+              u[j] = -INFINITY;
+              cnt[i] += 1.f;
+            }
+          }
+        }
+      }
+      const float mx = fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3]));
+      const float mn = fmaxf(m[i], mx);
+      const float msafe = (mn == -INFINITY) ? 0.f : mn;
+      float sum = s[i] * ex2_approx(m[i] - msafe);
+#pragma unroll
+      for (int j = 0; j < PR_TN; ++j) sum += ex2_approx(u[j] - msafe);
+      s[i] = sum;
+      m[i] = mn;
+    }
+    __syncthreads();  // everyone is done with stage `buf` before it is refilled
+  }
+
+  // merge the 16 column-group threads of each row: 8 lanes (xor 1,2,4) then the warp pair
+#pragma unroll
+  for (int i = 0; i < PR_TM; ++i) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m[i], o);
+      const float s2 = __shfl_xor_sync(0xffffffffu, s[i], o);
+      const float c2 = __shfl_xor_sync(0xffffffffu, cnt[i], o);
+      lse2_merge(m[i], s[i], m2, s2);
+      cnt[i] += c2;
+    }
+    if ((lane & 7) == 0) red[(ty + 16 * i) * 2 + (warp & 1)] = make_float4(m[i], s[i], cnt[i], 0.f);
+  }
+  __syncthreads();
+  if (tid < PR_BM) {
+    const int b = rb * PR_BM + tid;
+    float4 a = red[tid * 2 + 0];
+    const float4 c = red[tid * 2 + 1];
+    lse2_merge(a.x, a.y, c.x, c.y);
+    a.z += c.z;
+    reinterpret_cast<float4*>(part)[(size_t)b * nsplit + split] = a;
+  }
+}
+
+// merge P partials per row.  FINAL: also apply the row constants and the normaliser.
+//   log_p = cst - 0.5||zs||^2 + ln2*(M + log2 S) - log(C_total - n_masked)
+template <bool FINAL>
+__global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ part, int P, size_t row_stride,
+                                                        size_t part_stride, int B, const float* __restrict__ z,
+                                                        const float* __restrict__ logvar, int D, float c_total,
+                                                        float* __restrict__ out_stats, float* __restrict__ log_p,
+                                                        float* __restrict__ lse2) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float m = -INFINITY, s = 0.f, cnt = 0.f;
+  for (int p = lane; p < P; p += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (size_t)b * row_stride + (size_t)p * part_stride);
+    lse2_merge(m, s, v.x, v.y);
+    cnt += v.z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    lse2_merge(m, s, m2, s2);
+  }
+  if (!FINAL) {
+    if (lane == 0) reinterpret_cast<float4*>(out_stats)[b] = make_float4(m, s, cnt, 0.f);
+    return;
+  }
+  float hz = 0.f, cst = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float lv = logvar[d];
+    const float v = z[(size_t)b * D + d] / expf(0.5f * lv);
+    hz = fmaf(v, v, hz);
+    cst += lv + kLog2Pi;
+  }
+  hz = 0.5f * warp_sum(hz);
+  cst = -0.5f * warp_sum(cst);
+  if (lane == 0) {
+    const float l2 = m + log2f(s);
+    lse2[b] = l2;
+    log_p[b] = (cst - hz) + kLn2 * l2 - logf(c_total - cnt);
+  }
+}
+
+// ------------------------------------------------------------------------------- backward
+struct BwdSmem {
+  int zt, mt, ci, nb, w, gl, ll, red, bar, total;
+};
+constexpr int PR_WP = PR_BN + 1;  // W' pitch (floats): column reads by consecutive rows are conflict-free
+__host__ __device__ inline BwdSmem bwd_smem_layout(int LD) {
+  BwdSmem s;
+  int off = 0;
+  s.zt = off; off += PR_BM * LD * 4;
+  s.mt = off; off += PR_BN * LD * 4;
+  s.ci = off; off += PR_BN * 8;
+  s.nb = off; off += PR_BN * 4;
+  s.w = off;  off += (PR_BM * PR_WP * 4 + 15) / 16 * 16;
+  s.gl = off; off += PR_BM * 4;
+  s.ll = off; off += PR_BM * 4;
+  s.red = off; off += 8 * LD * 4;  // [8 warps][LD]
+  s.bar = off; off += 2 * 8;
+  s.total = off;
+  return s;
+}
+
+// One CTA owns one tile of PR_BN exemplar columns and walks all row blocks:
+//   P1  W'[b,n] = g_b * 2^(logit2[b,n] - lse2_b)   (recomputed, masked -> 0)      -> smem
+//   P2a dms[n,:] += sum_b W'[b,n] zs[b,:]  (registers, across row blocks)   colsum[n] += W'
+//   P2b dzs_part[tile][b,:] = sum_n W'[b,n] ms[n,:]                          rowsum_part = sum_n W'
+// then dmu[n,:] = (dms[n,:] - ms[n,:]*colsum[n]) / sigma   and the tile's share of sum_n dms.ms.
+template <bool MASK, int KCH_MAX>
+__global__ void __launch_bounds__(PR_THREADS, 2)
+    prior_lse_bwd_kernel(const float* __restrict__ zs, const float* __restrict__ ms, const float* __restrict__ nb2,
+                         const int64_t* __restrict__ cidx, const int64_t* __restrict__ z_idx,
+                         const float* __restrict__ lse2, const float* __restrict__ g, const float* __restrict__ isig,
+                         int B, int C, int D, int LD, int kch, int Bpad, float* __restrict__ dmu,
+                         float* __restrict__ dzs_part, float* __restrict__ rowsum_part,
+                         float* __restrict__ coldot_part) {
+  constexpr int MAXA = KCH_MAX / 4;  // chunks per thread in P2a (4 chunk groups)
+  constexpr int MAXB = KCH_MAX / 2;  // chunks per thread in P2b (2 chunk groups)
+  extern __shared__ __align__(128) unsigned char smem[];
+  const BwdSmem L = bwd_smem_layout(LD);
+  float* zt = reinterpret_cast<float*>(smem + L.zt);
+  float* mt = reinterpret_cast<float*>(smem + L.mt);
+  long long* cis = reinterpret_cast<long long*>(smem + L.ci);
+  float* nbs = reinterpret_cast<float*>(smem + L.nb);
+  float* W = reinterpret_cast<float*>(smem + L.w);
+  float* gl = reinterpret_cast<float*>(smem + L.gl);
+  float* ll = reinterpret_cast<float*>(smem + L.ll);
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = (lane & 7) + 8 * (warp & 1);
+  const int ty = (lane >> 3) + 4 * (warp >> 1);
+  const int tile = blockIdx.x;
+  const int LD4 = LD >> 2;
+  const int nrb = Bpad / PR_BM;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar[0], PR_BN * LD * 4 + PR_BN * 4 + PR_BN * 8);
+    bulk_g2s(mt, ms + (size_t)tile * PR_BN * LD, PR_BN * LD * 4, &bar[0]);
+    bulk_g2s(nbs, nb2 + (size_t)tile * PR_BN, PR_BN * 4, &bar[0]);
+    bulk_g2s(cis, cidx + (size_t)tile * PR_BN, PR_BN * 8, &bar[0]);
+  }
+
+  const float4* zt4 = reinterpret_cast<const float4*>(zt);
+  const float4* mt4 = reinterpret_cast<const float4*>(mt);
+
+  // P2a ownership: column ca, chunk group qa (warp-uniform)
+  const int ca = tid & (PR_BN - 1), qa = tid >> 6;
+  float4 accA[MAXA];
+#pragma unroll
+  for (int i = 0; i < MAXA; ++i) accA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float colsum = 0.f;
+  // P2b ownership: row rbw, chunk group hb (warp-uniform)
+  const int rbw = tid & (PR_BM - 1), hb = tid >> 7;
+
+  for (int rb = 0; rb < nrb; ++rb) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar[1], PR_BM * LD * 4);
+      bulk_g2s(zt, zs + (size_t)rb * PR_BM * LD, PR_BM * LD * 4, &bar[1]);
+    }
+    if (tid < PR_BM) {
+      const int b = rb * PR_BM + tid;
+      gl[tid] = b < B ? g[b] : 0.f;
+      ll[tid] = b < B ? lse2[b] : INFINITY;  // +inf => weight exactly 0 for padded rows
+    }
+    if (rb == 0) mbar_wait(&bar[0], 0);
+    mbar_wait(&bar[1], rb & 1);
+    __syncthreads();
+
+    // ---- P1
+    {
+      float acc[PR_TM][PR_TN];
+      tile_dot(zt4, mt4, LD4, kch, ty, tx, acc);
+      float nbv[PR_TN];
+      long long cj[PR_TN];
+#pragma unroll
+      for (int j = 0; j < PR_TN; ++j) {
+        nbv[j] = nbs[tx + 16 * j];
+        cj[j] = MASK ? cis[tx + 16 * j] : 0;
+      }
+#pragma unroll
+      for (int i = 0; i < PR_TM; ++i) {
+        const int r = ty + 16 * i;
+        const float gi = gl[r], li = ll[r];
+        long long zi = kPadIdx;
+        if (MASK) {
+          const int b = rb * PR_BM + r;
+          zi = b < B ? z_idx[b] : kPadIdx;
+        }
+#pragma unroll
+        for (int j = 0; j < PR_TN; ++j) {
+          float u = fmaf(acc[i][j], kLog2e, nbv[j]);
+          float w = gi * ex2_approx(u - li);
+          if (MASK) {
+            if (cj[j] == zi && cj[j] != kPadIdx) w = 0.f;
+          }
+          if (li == -INFINITY) w = 0.f;  // fully masked row: reference yields NaN; keep grads finite-free of inf*0
+          W[r * PR_WP + tx + 16 * j] = w;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- P2a: dms (registers) and colsum
+#pragma unroll 4
+    for (int b = 0; b < PR_BM; ++b) {
+      const float w = W[b * PR_WP + ca];
+      colsum += w;
+#pragma unroll
+      for (int i = 0; i < MAXA; ++i) {
+        const int k = qa + 4 * i;
+        if (k < kch) {
+          const float4 v = zt4[b * LD4 + k];
+          accA[i].x = fmaf(w, v.x, accA[i].x);
+          accA[i].y = fmaf(w, v.y, accA[i].y);
+          accA[i].z = fmaf(w, v.z, accA[i].z);
+          accA[i].w = fmaf(w, v.w, accA[i].w);
+        }
+      }
+    }
+    // ---- P2b: dzs partial for this (tile, row block)
+    {
+      float4 accB[MAXB];
+#pragma unroll
+      for (int i = 0; i < MAXB; ++i) accB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float rowsum = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < PR_BN; ++c) {
+        const float w = W[rbw * PR_WP + c];
+        rowsum += w;
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int k = hb + 2 * i;
+          if (k < kch) {
+            const float4 v = mt4[c * LD4 + k];
+            accB[i].x = fmaf(w, v.x, accB[i].x);
+            accB[i].y = fmaf(w, v.y, accB[i].y);
+            accB[i].z = fmaf(w, v.z, accB[i].z);
+            accB[i].w = fmaf(w, v.w, accB[i].w);
+          }
+        }
+      }
+      const size_t row = (size_t)tile * Bpad + (size_t)rb * PR_BM + rbw;
+      float4* dst = reinterpret_cast<float4*>(dzs_part + row * LD);
+#pragma unroll
+      for (int i = 0; i < MAXB; ++i) {
+        const int k = hb + 2 * i;
+        if (k < kch) dst[k] = accB[i];
+      }
+      if (hb == 0) rowsum_part[row] = rowsum;
+    }
+    __syncthreads();  // W, zt, gl, ll are rewritten by the next row block
+  }
+
+  // ---- epilogue: dmu and this tile's share of sum_n dms[n,d]*ms[n,d]
+  const int col = tile * PR_BN + ca;
+#pragma unroll
+  for (int i = 0; i < MAXA; ++i) {
+    const int k = qa + 4 * i;
+    if (k < kch) {  // warp-uniform
+      const float4 mv = mt4[ca * LD4 + k];
+      float4 d;
+      d.x = accA[i].x - mv.x * colsum;
+      d.y = accA[i].y - mv.y * colsum;
+      d.z = accA[i].z - mv.z * colsum;
+      d.w = accA[i].w - mv.w * colsum;
+      if (col < C) {
+        const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int dd = 4 * k + e;
+          if (dd < D) dmu[(size_t)col * D + dd] = dv[e] * isig[dd];
+        }
+      }
+      float p0 = d.x * mv.x, p1 = d.y * mv.y, p2 = d.z * mv.z, p3 = d.w * mv.w;
+      p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2); p3 = warp_sum(p3);
+      if (lane == 0) {
+        float* rr = red + warp * LD + 4 * k;
+        rr[0] = p0; rr[1] = p1; rr[2] = p2; rr[3] = p3;
+      }
+    }
+  }
+  __syncthreads();
+  // chunk k lives in warps 2*(k&3) and 2*(k&3)+1 (the two halves of the 64 columns)
+  for (int d = tid; d < 4 * kch; d += PR_THREADS) {
+    const int k = d >> 2, q = k & 3;
+    coldot_part[(size_t)tile * LD + d] = red[(2 * q) * LD + d] + red[(2 * q + 1) * LD + d];
+  }
+}
+
+// rows: dz = (sum_tiles dzs_part - zs * rowsum) / sigma ; rowdot = dzs * zs ; rs = rowsum
+__global__ void __launch_bounds__(256) prior_bwd_rows_kernel(const float* __restrict__ dzs_part,
+                                                             const float* __restrict__ rowsum_part,
+                                                             const float* __restrict__ zs,
+                                                             const float* __restrict__ isig, int ntile, int B, int D,
+                                                             int LD, int Bpad, float* __restrict__ dz,
+                                                             float* __restrict__ rowdot, float* __restrict__ rs) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float r = 0.f;
+  for (int t = lane; t < ntile; t += 32) r += rowsum_part[(size_t)t * Bpad + b];
+  r = warp_sum(r);
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    if (d < D) {
+      float acc = 0.f;
+      for (int t = 0; t < ntile; ++t) acc += dzs_part[((size_t)t * Bpad + b) * LD + d];
+      const float zv = zs[(size_t)b * LD + d];
+      const float dzs = acc - zv * r;
+      dz[(size_t)b * D + d] = dzs * isig[d];
+      rowdot[(size_t)b * LD + d] = dzs * zv;
+    }
+  }
+  if (lane == 0) rs[b] = r;
+}
+
+// dlogvar[d] = -0.5 * ( sum_b rs[b] + sum_b rowdot[b,d] + sum_tile coldot_part[tile,d] )
+__global__ void __launch_bounds__(1024) prior_bwd_dlogvar_kernel(const float* __restrict__ rs,
+                                                                 const float* __restrict__ rowdot,
+                                                                 const float* __restrict__ coldot_part, int B,
+                                                                 int ntile, int D, int LD,
+                                                                 float* __restrict__ dlogvar) {
+  __shared__ float sh[32];
+  __shared__ float s_rs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float a = 0.f;
+  for (int b = tid; b < B; b += blockDim.x) a += rs[b];
+  a = warp_sum(a);
+  if (lane == 0) sh[warp] = a;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    s_rs = t;
+  }
+  __syncthreads();
+  // one warp per dimension (strided), lanes over rows/tiles
+  for (int d = warp; d < D; d += (blockDim.x >> 5)) {
+    float acc = 0.f;
+    for (int b = lane; b < B; b += 32) acc += rowdot[(size_t)b * LD + d];
+    for (int t = lane; t < ntile; t += 32) acc += coldot_part[(size_t)t * LD + d];
+    acc = warp_sum(acc);
+    if (lane == 0) dlogvar[d] = -0.5f * (s_rs + acc);
+  }
+}
+
+int stage(const PriorWs& w, const float* z, const float* mu, const float* logvar, const int64_t* mu_idx, int B, int C,
+          int D, cudaStream_t st) {
+  const int rows = w.Cpad + w.Bpad;
+  prior_stage_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, mu, logvar, mu_idx, B, C, D, w.LD, w.Bpad, w.Cpad, w.zs,
+                                                        w.hz, w.ms, w.nb2, w.cidx, w.isig);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EXVAE_OK : (int)e;
+}
+
+}  // namespace
+}  // namespace exvae
+
+using namespace exvae;
+
+extern "C" size_t exvae_prior_lse_workspace_bytes(int B, int C, int D) {
+  if (B <= 0 || C <= 0 || D <= 0) return 0;
+  return prior_ws_layout(B, C, D, true, nullptr).bytes;
+}
+
+extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
+                                   const int64_t* mu_idx, int B, int C, int D, float* stats, void* ws, size_t ws_bytes,
+                                   exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(z && mu && logvar && stats && ws);
+  EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
+  if (D > 128) return EXVAE_ERR_UNSUPPORTED;
+  const PriorWs w = prior_ws_layout(B, C, D, true, ws);
+  // fwd only touches the leading (fwd) part of the layout: accept a fwd-only sized workspace too
+  const size_t need = prior_ws_layout(B, C, D, false, nullptr).bytes;
+  if (ws_bytes < need) return EXVAE_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, st);
+  if (rc) return rc;
+  const bool mask = z_idx && mu_idx;
+  const FwdSmem L = fwd_smem_layout(w.LD);
+  dim3 grid(w.nsplit, w.Bpad / PR_BM);
+  if (mask) {
+    EXVAE_CUDA(cudaFuncSetAttribute(prior_lse_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    prior_lse_fwd_kernel<true><<<grid, PR_THREADS, L.total, st>>>(w.zs, w.ms, w.nb2, w.cidx, z_idx, B, C, w.LD, w.kch,
+                                                                  w.ntile, w.nsplit, w.part);
+  } else {
+    EXVAE_CUDA(cudaFuncSetAttribute(prior_lse_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    prior_lse_fwd_kernel<false><<<grid, PR_THREADS, L.total, st>>>(w.zs, w.ms, w.nb2, w.cidx, z_idx, B, C, w.LD, w.kch,
+                                                                   w.ntile, w.nsplit, w.part);
+  }
+  EXVAE_CUDA(cudaGetLastError());
+  lse_merge_kernel<false><<<ceil_div(B, 8), 256, 0, st>>>(w.part, w.nsplit, (size_t)w.nsplit * 4, 4, B, nullptr,
+                                                          nullptr, D, 0.f, stats, nullptr, nullptr);
+  EXVAE_RETURN_LAST_ERROR();
+}
+
+extern "C" int exvae_prior_lse_finalize(const float* stats, int G, const float* z, const float* logvar, int B, int D,
+                                        int64_t C_total, float* log_p, float* lse2, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(stats && z && logvar && log_p && lse2);
+  EXVAE_CHECK_ARG(G > 0 && B > 0 && D > 0 && C_total > 0);
+  lse_merge_kernel<true><<<ceil_div(B, 8), 256, 0, as_stream(stream)>>>(stats, G, 4, (size_t)B * 4, B, z, logvar, D,
+                                                                        (float)C_total, nullptr, log_p, lse2);
+  EXVAE_RETURN_LAST_ERROR();
+}
+
+extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
+                                   const int64_t* mu_idx, int B, int C, int D, const float* lse2,
+                                   const float* grad_log_p, float* dz, float* dmu, float* dlogvar, void* ws,
+                                   size_t ws_bytes, int ws_prepared, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(z && mu && logvar && lse2 && grad_log_p && dz && dmu && dlogvar && ws);
+  EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
+  if (D > 128) return EXVAE_ERR_UNSUPPORTED;
+  const PriorWs w = prior_ws_layout(B, C, D, true, ws);
+  if (ws_bytes < w.bytes) return EXVAE_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (!ws_prepared) {
+    int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, st);
+    if (rc) return rc;
+  }
+  const bool mask = z_idx && mu_idx;
+  const BwdSmem L = bwd_smem_layout(w.LD);
+  auto launch = [&](auto kern) -> int {
+    EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    kern<<<w.ntile, PR_THREADS, L.total, st>>>(w.zs, w.ms, w.nb2, w.cidx, z_idx, lse2, grad_log_p, w.isig, B, C, D,
+                                               w.LD, w.kch, w.Bpad, dmu, w.dzs_part, w.rowsum_part, w.coldot_part);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? EXVAE_OK : (int)e;
+  };
+  int rc;
+  if (w.kch <= 12)
+    rc = mask ? launch(prior_lse_bwd_kernel<true, 12>) : launch(prior_lse_bwd_kernel<false, 12>);
+  else
+    rc = mask ? launch(prior_lse_bwd_kernel<true, 32>) : launch(prior_lse_bwd_kernel<false, 32>);
+  if (rc) return rc;
+  prior_bwd_rows_kernel<<<ceil_div(B, 8), 256, 0, st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, w.ntile, B, D, w.LD,
+                                                        w.Bpad, dz, w.rowdot, w.rs);
+  EXVAE_CUDA(cudaGetLastError());
+  prior_bwd_dlogvar_kernel<<<1, 1024, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, w.ntile, D, w.LD, dlogvar);
+  EXVAE_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,600 @@
+"""torch.autograd bindings of the exvae_b200 C ABI.
+
+PyTorch is plumbing here: it owns device memory, the current stream and the autograd tape;
+every arithmetic step is a kernel of ``csrc/libexvae_b200.so`` launched on
+``torch.cuda.current_stream()`` (so whole training steps can be captured in a CUDA graph).
+Inputs must be CUDA tensors — a CPU tensor raises; there is no CPU code path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import ACT_HARDTANH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ExvaeError, lib
+
+__all__ = [
+    "prior_lse", "pairwise_distance", "log_normal_diag_vectorized", "prior_logprob_matrix", "knn_topk", "knn_merge",
+    "unique_positions", "gather_rows", "scatter_rows_", "gated_dense", "linear", "reparameterize",
+    "log_normal_diag", "log_normal_standard", "log_bernoulli", "log_logistic_256", "elbo_reduce",
+    "rng_bernoulli", "rng_normal", "rng_randint", "launch_count", "reset_launch_count",
+]
+
+_LAUNCHES = 0  # number of exvae kernels enqueued through this module (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def reset_launch_count() -> None:
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str = "tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise ExvaeError(f"{name} must be a CUDA tensor: exemplar_vae_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise ExvaeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i64(t: Optional[torch.Tensor], name: str = "index") -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ExvaeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ======================================================================================
+# K1: fused exemplar prior
+# ======================================================================================
+class _PriorLSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group):
+        L = lib()
+        z, mu, logvar = _f32(z, "z"), _f32(mu, "mu"), _f32(logvar, "logvar")
+        B, D = z.shape
+        C = mu.shape[0]
+        assert mu.shape[1] == D and logvar.numel() == D
+        z_idx = _i64(z_idx)
+        mu_idx = _i64(mu_idx)
+        if z_idx is not None:
+            z_idx = z_idx.reshape(-1)
+            assert z_idx.numel() == B
+        if mu_idx is not None:
+            mu_idx = mu_idx.reshape(-1)
+            assert mu_idx.numel() == C
+        ws = _ws(L.exvae_prior_lse_workspace_bytes(B, C, D), z.device)
+        stats = torch.empty((B, 4), dtype=torch.float32, device=z.device)
+        L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(stats), _p(ws),
+                                      ws.numel(), _stream()), "prior_lse_fwd")
+        _count(3)
+        G = 1
+        all_stats = stats
+        if group is not None:
+            import torch.distributed as dist
+            G = dist.get_world_size(group)
+            all_stats = torch.empty((G, B, 4), dtype=torch.float32, device=z.device)
+            dist.all_gather_into_tensor(all_stats, stats, group=group)   # the single LSE-partial exchange
+        total = int(c_total) if c_total is not None else C
+        log_p = torch.empty((B,), dtype=torch.float32, device=z.device)
+        lse2 = torch.empty((B,), dtype=torch.float32, device=z.device)
+        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z), _p(logvar), B, D, total, _p(log_p), _p(lse2),
+                                           _stream()), "prior_lse_finalize")
+        _count(1)
+        ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws)
+        ctx.dims = (B, C, D)
+        return log_p
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        z, mu, logvar, z_idx, mu_idx, lse2, ws = ctx.saved_tensors
+        B, C, D = ctx.dims
+        g = _f32(g, "grad")
+        dz = torch.empty_like(z)
+        dmu = torch.empty_like(mu)
+        dlv = torch.empty((D,), dtype=torch.float32, device=z.device)
+        L.check(L.exvae_prior_lse_bwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(lse2), _p(g),
+                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _stream()), "prior_lse_bwd")
+        _count(3)
+        return dz, dmu, dlv.view_as(logvar), None, None, None, None
+
+
+def prior_lse(z, mu, logvar, z_idx=None, mu_idx=None, c_total=None, group=None) -> torch.Tensor:
+    """log p(z_b) = LSE_n log N(z_b | mu_n, exp(logvar)) - log(C - #masked_b)   -> [B].
+
+    ``logvar`` is the [D] log-variance vector shared by all exemplars.  ``z_idx``/``mu_idx``
+    enable the leave-one-out mask.  With ``group`` the bank ``mu`` is this rank's shard of a
+    range-sharded bank: partial (max, sum, count) statistics are all-gathered once and merged;
+    ``c_total`` is the global exemplar count.  dz/dlogvar gradients are then per-shard partials."""
+    return _PriorLSE.apply(z, mu, logvar, z_idx, mu_idx, c_total, group)
+
+
+# ======================================================================================
+# materialising primitives + kNN (no autograd: used for selection only)
+# ======================================================================================
+@torch.no_grad()
+def pairwise_distance(z, means) -> torch.Tensor:
+    L = lib()
+    z, means = _f32(z), _f32(means)
+    B, D = z.shape
+    C = means.shape[0]
+    out = torch.empty((B, C), dtype=torch.float32, device=z.device)
+    L.check(L.exvae_pairwise_distance(_p(z), _p(means), B, C, D, _p(out), _stream()), "pairwise_distance")
+    _count(1)
+    return out
+
+
+@torch.no_grad()
+def log_normal_diag_vectorized(x, mean, log_var) -> Tuple[torch.Tensor, torch.Tensor]:
+    L = lib()
+    x, mean = _f32(x), _f32(mean)
+    lv = _f32(log_var).reshape(-1)
+    B, D = x.shape
+    C = mean.shape[0]
+    assert lv.numel() == D
+    ln = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    pd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    L.check(L.exvae_log_normal_diag_vectorized(_p(x), _p(mean), _p(lv), B, C, D, _p(ln), _p(pd), _stream()),
+            "log_normal_diag_vectorized")
+    _count(1)
+    return ln, pd
+
+
+@torch.no_grad()
+def prior_logprob_matrix(z, mu, logvar, z_idx=None, mu_idx=None) -> torch.Tensor:
+    L = lib()
+    z, mu, logvar = _f32(z), _f32(mu), _f32(logvar).reshape(-1)
+    B, D = z.shape
+    C = mu.shape[0]
+    z_idx = _i64(z_idx)
+    mu_idx = _i64(mu_idx)
+    if z_idx is not None:
+        z_idx = z_idx.reshape(-1)
+    if mu_idx is not None:
+        mu_idx = mu_idx.reshape(-1)
+    out = torch.empty((B, C), dtype=torch.float32, device=z.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=z.device)
+    L.check(L.exvae_prior_logprob_matrix(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(out),
+                                         _p(counts), _stream()), "prior_logprob_matrix")
+    _count(2 if (z_idx is not None and mu_idx is not None) else 1)
+    return out
+
+
+@torch.no_grad()
+def knn_topk(z, bank, k: int, metric: int = 0, pos_offset: int = 0):
+    """k smallest distances per row -> (positions [B,k] int64, distances [B,k]).  metric 0 = the
+    reference's fp64-expansion squared distance (BaseModel.py:263), 1 = sqrt-Euclidean
+    (knn_on_latent.py:4-9)."""
+    L = lib()
+    z, bank = _f32(z), _f32(bank)
+    B, D = z.shape
+    C = bank.shape[0]
+    idx = torch.empty((B, k), dtype=torch.int64, device=z.device)
+    dist = torch.empty((B, k), dtype=torch.float32, device=z.device)
+    ws = _ws(L.exvae_knn_workspace_bytes(B, C, D, k), z.device)
+    L.check(L.exvae_knn_topk(_p(z), _p(bank), B, C, D, k, metric, pos_offset, _p(idx), _p(dist), _p(ws), ws.numel(),
+                             _stream()), "knn_topk")
+    _count(2)
+    return idx, dist
+
+
+@torch.no_grad()
+def knn_merge(idx, dist):
+    """Merge per-shard candidate lists [G,B,k] into the global k smallest."""
+    L = lib()
+    idx, dist = _i64(idx), _f32(dist)
+    G, B, k = idx.shape
+    oi = torch.empty((B, k), dtype=torch.int64, device=idx.device)
+    od = torch.empty((B, k), dtype=torch.float32, device=idx.device)
+    L.check(L.exvae_knn_merge(_p(idx), _p(dist), G, B, k, _p(oi), _p(od), _stream()), "knn_merge")
+    _count(1)
+    return oi, od
+
+
+@torch.no_grad()
+def unique_positions(pos, value_range: int):
+    """Sorted unique values of ``pos`` (all in [0, value_range)) -> (padded [n] int64, count [1] int32 on device)."""
+    L = lib()
+    pos = _i64(pos).reshape(-1)
+    n = pos.numel()
+    out = torch.empty((n,), dtype=torch.int64, device=pos.device)
+    count = torch.empty((1,), dtype=torch.int32, device=pos.device)
+    flags = torch.empty((value_range,), dtype=torch.int32, device=pos.device)
+    L.check(L.exvae_unique_positions(_p(pos), n, value_range, _p(out), _p(count), _p(flags), _stream()),
+            "unique_positions")
+    _count(1)
+    return out, count
+
+
+@torch.no_grad()
+def gather_rows(src, idx) -> torch.Tensor:
+    L = lib()
+    src = _f32(src)
+    idx = _i64(idx).reshape(-1)
+    n, row = idx.numel(), src.shape[1]
+    out = torch.empty((n, row), dtype=torch.float32, device=src.device)
+    if n:
+        L.check(L.exvae_gather_rows(_p(src), _p(idx), n, row, _p(out), _stream()), "gather_rows")
+        _count(1)
+    return out
+
+
+@torch.no_grad()
+def scatter_rows_(dst, idx, src) -> torch.Tensor:
+    """dst[idx] = src, in place (cache refresh, BaseModel.py:261,269)."""
+    L = lib()
+    assert dst.is_cuda and dst.dtype == torch.float32 and dst.is_contiguous()
+    src = _f32(src)
+    idx = _i64(idx).reshape(-1)
+    if idx.numel():
+        L.check(L.exvae_scatter_rows(_p(dst), _p(idx), idx.numel(), dst.shape[1], _p(src), _stream()), "scatter_rows")
+        _count(1)
+    return dst
+
+
+# ======================================================================================
+# K3: dense layers
+# ======================================================================================
+class _GatedDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wh, bh, Wg, bg):
+        L = lib()
+        x, Wh, Wg = _f32(x, "x"), _f32(Wh), _f32(Wg)
+        bh = _f32(bh) if bh is not None else None
+        bg = _f32(bg) if bg is not None else None
+        R, K = x.shape
+        O = Wh.shape[0]
+        out = torch.empty((R, O), dtype=torch.float32, device=x.device)
+        need = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, Wh, bh, Wg, bg))
+        h = torch.empty_like(out) if need else None
+        s = torch.empty_like(out) if need else None
+        L.check(L.exvae_gated_dense_fwd(_p(x), _p(Wh), _p(bh), _p(Wg), _p(bg), R, K, O, _p(out), _p(h), _p(s),
+                                        _stream()), "gated_dense_fwd")
+        _count(1)
+        ctx.save_for_backward(x, Wh, Wg, h, s)
+        ctx.has_bias = (bh is not None, bg is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        x, Wh, Wg, h, s = ctx.saved_tensors
+        dout = _f32(dout)
+        R, K = x.shape
+        O = Wh.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dWh, dWg = torch.empty_like(Wh), torch.empty_like(Wg)
+        dbh = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
+        dbg = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[1] else None
+        ws = _ws(L.exvae_gated_dense_bwd_workspace_bytes(R, K, O), x.device)
+        L.check(L.exvae_gated_dense_bwd(_p(x), _p(Wh), _p(Wg), _p(h), _p(s), _p(dout), R, K, O, _p(dx), _p(dWh),
+                                        _p(dbh), _p(dWg), _p(dbg), _p(ws), ws.numel(), _stream()), "gated_dense_bwd")
+        _count(5 + (1 if dx is not None else 0))
+        return dx, dWh, dbh, dWg, dbg
+
+
+def gated_dense(x, Wh, bh, Wg, bg) -> torch.Tensor:
+    """(x Wh^T + bh) * sigmoid(x Wg^T + bg)   (utils/nn.py:44-69)."""
+    return _GatedDense.apply(x, Wh, bh, Wg, bg)
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b, act, lo, hi):
+        L = lib()
+        x, W = _f32(x, "x"), _f32(W)
+        b = _f32(b) if b is not None else None
+        R, K = x.shape
+        O = W.shape[0]
+        out = torch.empty((R, O), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_linear_fwd(_p(x), _p(W), _p(b), R, K, O, act, lo, hi, _p(out), _stream()), "linear_fwd")
+        _count(1)
+        ctx.save_for_backward(x, W, out if act != ACT_NONE else None)
+        ctx.cfg = (act, lo, hi, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        x, W, out = ctx.saved_tensors
+        act, lo, hi, has_b = ctx.cfg
+        dout = _f32(dout)
+        R, K = x.shape
+        O = W.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(W)
+        db = torch.empty((O,), dtype=torch.float32, device=x.device) if has_b else None
+        ws = _ws(L.exvae_linear_bwd_workspace_bytes(R, K, O), x.device)
+        L.check(L.exvae_linear_bwd(_p(x), _p(W), _p(out), _p(dout), R, K, O, act, lo, hi, _p(dx), _p(dW), _p(db),
+                                   _p(ws), ws.numel(), _stream()), "linear_bwd")
+        _count(4 + (1 if dx is not None else 0) + (1 if act != ACT_NONE else 0))
+        return dx, dW, db, None, None, None
+
+
+def linear(x, W, b=None, act: int = ACT_NONE, lo: float = 0.0, hi: float = 0.0) -> torch.Tensor:
+    """act(x W^T + b)   (utils/nn.py:29-41)."""
+    return _Linear.apply(x, W, b, act, float(lo), float(hi))
+
+
+# ======================================================================================
+# element-wise pieces of the ELBO
+# ======================================================================================
+class _Reparam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        L = lib()
+        mu, logvar, eps = _f32(mu), _f32(logvar), _f32(eps)
+        z = torch.empty_like(mu)
+        L.check(L.exvae_reparameterize_fwd(_p(mu), _p(logvar), _p(eps), mu.numel(), _p(z), _stream()), "reparam_fwd")
+        _count(1)
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        L = lib()
+        logvar, eps = ctx.saved_tensors
+        dz = _f32(dz)
+        dmu = torch.empty_like(dz) if ctx.needs_input_grad[0] else None
+        dlv = torch.empty_like(dz) if ctx.needs_input_grad[1] else None
+        L.check(L.exvae_reparameterize_bwd(_p(logvar), _p(eps), _p(dz), dz.numel(), _p(dmu), _p(dlv), _stream()),
+                "reparam_bwd")
+        _count(1)
+        return dmu, dlv, None
+
+
+def reparameterize(mu, logvar, eps) -> torch.Tensor:
+    return _Reparam.apply(mu, logvar, eps)
+
+
+class _LogNormalDiag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, logvar):
+        L = lib()
+        x, mean, logvar = _f32(x), _f32(mean), _f32(logvar)
+        B, D = x.shape
+        out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_log_normal_diag_fwd(_p(x), _p(mean), _p(logvar), B, D, _p(out), _stream()), "log_normal_diag")
+        _count(1)
+        ctx.save_for_backward(x, mean, logvar)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        x, mean, logvar = ctx.saved_tensors
+        g = _f32(g)
+        B, D = x.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dm = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        dl = torch.empty_like(x) if ctx.needs_input_grad[2] else None
+        L.check(L.exvae_log_normal_diag_bwd(_p(x), _p(mean), _p(logvar), _p(g), B, D, _p(dx), _p(dm), _p(dl),
+                                            _stream()), "log_normal_diag_bwd")
+        _count(1)
+        return dx, dm, dl
+
+
+def log_normal_diag(x, mean, log_var) -> torch.Tensor:
+    """utils/distributions.py:28-33 with dim=1 (x, mean, log_var all [B, D])."""
+    return _LogNormalDiag.apply(x, mean, log_var)
+
+
+class _LogNormalStd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L = lib()
+        x = _f32(x)
+        B, D = x.shape
+        out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_log_normal_standard_fwd(_p(x), B, D, _p(out), _stream()), "log_normal_standard")
+        _count(1)
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        (x,) = ctx.saved_tensors
+        g = _f32(g)
+        B, D = x.shape
+        dx = torch.empty_like(x)
+        L.check(L.exvae_log_normal_standard_bwd(_p(x), _p(g), B, D, _p(dx), _stream()), "log_normal_standard_bwd")
+        _count(1)
+        return dx
+
+
+def log_normal_standard(x) -> torch.Tensor:
+    return _LogNormalStd.apply(x)
+
+
+class _LogBernoulli(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean):
+        L = lib()
+        x, mean = _f32(x), _f32(mean)
+        B, P = mean.shape
+        out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_log_bernoulli_fwd(_p(x), _p(mean), B, P, _p(out), _stream()), "log_bernoulli")
+        _count(1)
+        ctx.save_for_backward(x, mean)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        x, mean = ctx.saved_tensors
+        g = _f32(g)
+        B, P = mean.shape
+        dm = torch.empty_like(mean)
+        L.check(L.exvae_log_bernoulli_bwd(_p(x), _p(mean), _p(g), B, P, _p(dm), _stream()), "log_bernoulli_bwd")
+        _count(1)
+        return None, dm
+
+
+def log_bernoulli(x, mean) -> torch.Tensor:
+    """utils/distributions.py:44-51 with dim=1; gradient flows to ``mean`` only (x is data)."""
+    return _LogBernoulli.apply(x, mean)
+
+
+class _LogLogistic256(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, logvar):
+        L = lib()
+        x, mean, logvar = _f32(x), _f32(mean), _f32(logvar)
+        B, P = mean.shape
+        out = torch.empty((B,), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_log_logistic256_fwd(_p(x), _p(mean), _p(logvar), B, P, _p(out), _stream()), "log_logistic_256")
+        _count(1)
+        ctx.save_for_backward(x, mean, logvar)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        x, mean, logvar = ctx.saved_tensors
+        g = _f32(g)
+        B, P = mean.shape
+        dm = torch.empty_like(mean) if ctx.needs_input_grad[1] else None
+        dl = torch.empty_like(mean) if ctx.needs_input_grad[2] else None
+        L.check(L.exvae_log_logistic256_bwd(_p(x), _p(mean), _p(logvar), _p(g), B, P, _p(dm), _p(dl), _stream()),
+                "log_logistic_256_bwd")
+        _count(1)
+        return None, dm, dl
+
+
+def log_logistic_256(x, mean, logvar) -> torch.Tensor:
+    return _LogLogistic256.apply(x, mean, logvar)
+
+
+class _ElboReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, RE, KL, beta, average):
+        L = lib()
+        RE, KL = _f32(RE), _f32(KL)
+        B = RE.numel()
+        ctx.cfg = (B, float(beta), bool(average))
+        if average:
+            out3 = torch.empty((3,), dtype=torch.float32, device=RE.device)
+            L.check(L.exvae_elbo_reduce(_p(RE), _p(KL), B, beta, 1, _p(out3), None, _stream()), "elbo_reduce")
+            _count(1)
+            return out3
+        loss_b = torch.empty((B,), dtype=torch.float32, device=RE.device)
+        L.check(L.exvae_elbo_reduce(_p(RE), _p(KL), B, beta, 0, None, _p(loss_b), _stream()), "elbo_reduce")
+        _count(1)
+        return loss_b
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        B, beta, average = ctx.cfg
+        g = _f32(g)
+        dRE = torch.empty((B,), dtype=torch.float32, device=g.device)
+        dKL = torch.empty((B,), dtype=torch.float32, device=g.device)
+        L.check(L.exvae_elbo_reduce_bwd(_p(g) if average else None, None if average else _p(g), B, beta,
+                                        1 if average else 0, _p(dRE), _p(dKL), _stream()), "elbo_reduce_bwd")
+        _count(1)
+        return dRE, dKL, None, None
+
+
+def elbo_reduce(RE, KL, beta: float, average: bool):
+    """models/BaseModel.py:71-75.  average=True -> tensor [3] = (mean loss, mean RE, mean KL);
+    average=False -> per-sample loss [B]."""
+    return _ElboReduce.apply(RE, KL, float(beta), bool(average))
+
+
+# ======================================================================================
+# counter-based RNG
+# ======================================================================================
+@torch.no_grad()
+def rng_bernoulli(p, seed: int, counter: Optional[torch.Tensor], subseq: int) -> torch.Tensor:
+    L = lib()
+    p = _f32(p)
+    out = torch.empty_like(p)
+    L.check(L.exvae_rng_bernoulli(_p(p), p.numel(), seed, _p(counter), subseq, _p(out), _stream()), "rng_bernoulli")
+    _count(1)
+    return out
+
+
+@torch.no_grad()
+def rng_normal(shape, seed: int, counter: Optional[torch.Tensor], subseq: int, device) -> torch.Tensor:
+    L = lib()
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    L.check(L.exvae_rng_normal(out.numel(), seed, _p(counter), subseq, _p(out), _stream()), "rng_normal")
+    _count(1)
+    return out
+
+
+@torch.no_grad()
+def rng_randint(low: int, high: int, n: int, seed: int, counter: Optional[torch.Tensor], subseq: int, device):
+    L = lib()
+    out = torch.empty((n,), dtype=torch.int64, device=device)
+    L.check(L.exvae_rng_randint(low, high, n, seed, _p(counter), subseq, _p(out), _stream()), "rng_randint")
+    _count(1)
+    return out
+
+
+@torch.no_grad()
+def rng_advance_(counter: torch.Tensor, by: int = 1) -> None:
+    L = lib()
+    L.check(L.exvae_rng_advance(_p(counter), by, _stream()), "rng_advance")
+    _count(1)
+
+
+class _LinComb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coeffs, *xs):
+        L = lib()
+        xs = [_f32(x) for x in xs]
+        assert 1 <= len(xs) <= 4 and len(coeffs) == len(xs)
+        ctx.coeffs = tuple(float(c) for c in coeffs)
+        out = torch.empty_like(xs[0])
+        ptrs = [_p(x) for x in xs] + [None] * (4 - len(xs))
+        cs = list(ctx.coeffs) + [0.0] * (4 - len(xs))
+        L.check(L.exvae_lincomb4(*ptrs, *cs, out.numel(), _p(out), _stream()), "lincomb4")
+        _count(1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        g = _f32(g)
+        grads = []
+        for i, c in enumerate(ctx.coeffs):
+            if not ctx.needs_input_grad[i + 1]:
+                grads.append(None)
+                continue
+            d = torch.empty_like(g)
+            L.check(L.exvae_lincomb4(_p(g), None, None, None, c, 0.0, 0.0, 0.0, g.numel(), _p(d), _stream()),
+                    "lincomb4_bwd")
+            _count(1)
+            grads.append(d)
+        return (None, *grads)
+
+
+def lincomb(coeffs, *xs) -> torch.Tensor:
+    """sum_j coeffs[j] * xs[j] for up to four same-shaped tensors (KL assembly)."""
+    return _LinComb.apply(tuple(coeffs), *xs)

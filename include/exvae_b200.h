@@ -1,0 +1,205 @@
+/* exvae_b200 — C ABI of the B200-native (sm_100a) Exemplar-VAE hot path.
+ *
+ * The reference (sajadn/Exemplar-VAE) is pure Python/PyTorch and prescribes no FFI; its plug
+ * points are Python call sites.  Each entry point below replaces the arithmetic behind one
+ * of those call sites (cited as reference `file:line`); the Python package
+ * `exemplar_vae_b200` binds them with ctypes and re-exposes the reference's own function
+ * and class names.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless a parameter says "host".  The caller owns every
+ *    buffer; the library allocates nothing.  Scratch memory is passed in as `ws`/`ws_bytes`
+ *    (query the matching *_workspace_bytes function; 256-byte aligned).
+ *  - Tensors are contiguous row-major fp32; indices are int64 (torch.long).
+ *  - All work is enqueued on `stream` (a cudaStream_t); no call synchronises the host, so
+ *    every call is legal inside CUDA-graph capture.  The library is stateless/re-entrant.
+ *  - Return value: 0 = ok; <0 = argument/capability error (EXVAE_ERR_*); >0 = cudaError_t
+ *    of the failed launch.  No C++ exception crosses this boundary.
+ */
+#ifndef EXVAE_B200_H_
+#define EXVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* exvae_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define EXVAE_API __attribute__((visibility("default")))
+#else
+#define EXVAE_API
+#endif
+
+#define EXVAE_OK 0
+#define EXVAE_ERR_INVALID_ARG (-1)
+#define EXVAE_ERR_UNSUPPORTED (-2)
+#define EXVAE_ERR_WORKSPACE (-3)
+
+#define EXVAE_ABI_VERSION 1
+
+/* activation codes for exvae_linear_* (utils/nn.py:29-41 NonLinear) */
+#define EXVAE_ACT_NONE 0
+#define EXVAE_ACT_SIGMOID 1
+#define EXVAE_ACT_HARDTANH 2
+#define EXVAE_ACT_RELU 3
+
+EXVAE_API int exvae_abi_version(void);
+EXVAE_API const char* exvae_error_string(int code);
+/* host out-params; fails with a cudaError_t if no device is usable */
+EXVAE_API int exvae_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- exemplar prior (K1)
+ * Fused replacement of  log_normal_diag_vectorized -> pairwise_distance
+ * (utils/distributions.py:12-25), the leave-one-out mask and normaliser
+ * (models/BaseModel.py:98-109) and the max-shifted log-sum-exp (models/BaseModel.py:123-125).
+ *
+ *   z [B,D], mu [C,D], logvar [D] (row 0 of the reference's [C,D] log-variance bank,
+ *   BaseModel.py:101), z_idx [B] / mu_idx [C] dataset indices or NULL (either NULL => no mask,
+ *   i.e. test mode / no_mask, BaseModel.py:103).
+ *
+ * fwd writes per-row partial statistics of THIS bank shard: stats[b] = (m2, s2, n_masked, 0)
+ * with  sum_n exp(logit[b,n]) = 2^m2 * s2 * exp(c_b)  (c_b is a row constant applied in
+ * finalize).  finalize merges the stats of G shards ([G,B,4], G=1 on one GPU) into
+ *   log_p[b] = LSE_n logit[b,n] - log(C_total - n_masked_b)          (BaseModel.py:107-108,125)
+ * and lse2[b] (base-2 row log-sum, saved for the backward).
+ * bwd: given dL/dlog_p returns dz [B,D] (partial over this shard), dmu [C,D] (complete for
+ * this shard) and dlogvar [D] (partial over this shard).
+ */
+EXVAE_API size_t exvae_prior_lse_workspace_bytes(int B, int C, int D);
+EXVAE_API int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
+                        const int64_t* mu_idx, int B, int C, int D, float* stats /*[B,4]*/, void* ws,
+                        size_t ws_bytes, exvae_stream_t stream);
+EXVAE_API int exvae_prior_lse_finalize(const float* stats /*[G,B,4]*/, int G, const float* z, const float* logvar, int B, int D,
+                             int64_t C_total, float* log_p /*[B]*/, float* lse2 /*[B]*/, exvae_stream_t stream);
+/* ws must be the workspace a fwd call with the same arguments filled (ws_prepared=1) or any
+ * workspace of the right size (ws_prepared=0: the bank is re-staged). */
+EXVAE_API int exvae_prior_lse_bwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
+                        const int64_t* mu_idx, int B, int C, int D, const float* lse2, const float* grad_log_p,
+                        float* dz, float* dmu, float* dlogvar, void* ws, size_t ws_bytes, int ws_prepared,
+                        exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- materialising primitives
+ * pairwise_distance (utils/distributions.py:12-18): fp64 inside, fp32 [B,C] out.            */
+EXVAE_API int exvae_pairwise_distance(const float* z, const float* means, int B, int C, int D, float* out,
+                            exvae_stream_t stream);
+/* log_normal_diag_vectorized (utils/distributions.py:21-25); log_var [D]; pair_dist may be NULL */
+EXVAE_API int exvae_log_normal_diag_vectorized(const float* x, const float* mean, const float* log_var, int B, int C, int D,
+                                     float* log_normal, float* pair_dist, exvae_stream_t stream);
+/* log_p_z_exemplar with sum=False (models/BaseModel.py:98-109,126-127): [B,C] matrix with -inf at
+ * masked pairs and -log(C - n_masked_b) applied.  row_counts: scratch [B] int32. */
+EXVAE_API int exvae_prior_logprob_matrix(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
+                               const int64_t* mu_idx, int B, int C, int D, float* out, int* row_counts,
+                               exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- kNN exemplar selection (K2)
+ * pairwise_distance(z, bank).topk(k, largest=False) (models/BaseModel.py:263-264): fp64
+ * expansion distance rounded to fp32, k smallest per row sorted ascending, ties -> lowest
+ * position.  metric 1 = direct-difference fp32 Euclidean with sqrt (utils/knn_on_latent.py:4-9).
+ * pos_offset is added to every returned position (bank shards).                                */
+EXVAE_API size_t exvae_knn_workspace_bytes(int B, int C, int D, int k);
+EXVAE_API int exvae_knn_topk(const float* z, const float* bank, int B, int C, int D, int k, int metric, int64_t pos_offset,
+                   int64_t* out_idx /*[B,k]*/, float* out_dist /*[B,k]*/, void* ws, size_t ws_bytes,
+                   exvae_stream_t stream);
+/* merge G per-shard candidate lists [G,B,k] into the global k smallest per row */
+EXVAE_API int exvae_knn_merge(const int64_t* idx, const float* dist, int G, int B, int k, int64_t* out_idx, float* out_dist,
+                    exvae_stream_t stream);
+/* torch.unique(positions) (models/BaseModel.py:265) for positions in [0, range): ascending unique
+ * values in out[0..count) (capacity n), count written to *out_count (device int32).
+ * flags: scratch [range] int32.                                                                  */
+EXVAE_API int exvae_unique_positions(const int64_t* pos, int n, int range, int64_t* out, int* out_count, int* flags,
+                           exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- row movement
+ * dataset.tensors[0][idx] (models/BaseModel.py:247,267), cached_z[idx] (:262) and the cache
+ * refresh cached_z[idx] = rows (:261,:269).                                                     */
+EXVAE_API int exvae_gather_rows(const float* src, const int64_t* idx, int n_rows, int row_len, float* out,
+                      exvae_stream_t stream);
+EXVAE_API int exvae_scatter_rows(float* dst, const int64_t* idx, int n_rows, int row_len, const float* src,
+                       exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- dense layers (K3)
+ * GatedDense (utils/nn.py:44-69): out = (x Wh^T + bh) * sigmoid(x Wg^T + bg).
+ * x [R,K], Wh/Wg [O,K], out [R,O].  h_lin/sig [R,O] are saved for the backward (NULL to skip).   */
+EXVAE_API int exvae_gated_dense_fwd(const float* x, const float* Wh, const float* bh, const float* Wg, const float* bg, int R,
+                          int K, int O, float* out, float* h_lin, float* sig, exvae_stream_t stream);
+EXVAE_API size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O);
+/* dx may be NULL (first layer: the input is data). */
+EXVAE_API int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin, const float* sig,
+                          const float* dout, int R, int K, int O, float* dx, float* dWh, float* dbh, float* dWg,
+                          float* dbg, void* ws, size_t ws_bytes, exvae_stream_t stream);
+/* nn.Linear / NonLinear (utils/nn.py:29-41): out = act(x W^T + b); b may be NULL. */
+EXVAE_API int exvae_linear_fwd(const float* x, const float* W, const float* b, int R, int K, int O, int act, float lo, float hi,
+                     float* out, exvae_stream_t stream);
+EXVAE_API size_t exvae_linear_bwd_workspace_bytes(int R, int K, int O);
+/* `out` is the forward OUTPUT (post activation); dx / db may be NULL. */
+EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out, const float* dout, int R, int K, int O, int act,
+                     float lo, float hi, float* dx, float* dW, float* db, void* ws, size_t ws_bytes,
+                     exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- element-wise pieces
+ * reparameterize (models/BaseModel.py:79-82): z = mu + exp(0.5 logvar) * eps (eps injected). */
+EXVAE_API int exvae_reparameterize_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, float* z,
+                             exvae_stream_t stream);
+EXVAE_API int exvae_reparameterize_bwd(const float* logvar, const float* eps, const float* dz, int64_t n, float* dmu,
+                             float* dlogvar, exvae_stream_t stream);
+/* log_normal_diag(x, mean, log_var, dim=1) (utils/distributions.py:28-33): out [B]. */
+EXVAE_API int exvae_log_normal_diag_fwd(const float* x, const float* mean, const float* logvar, int B, int D, float* out,
+                              exvae_stream_t stream);
+EXVAE_API int exvae_log_normal_diag_bwd(const float* x, const float* mean, const float* logvar, const float* dout, int B, int D,
+                              float* dx, float* dmean, float* dlogvar, exvae_stream_t stream);
+/* log_normal_standard(x, dim=1) (utils/distributions.py:36-41) */
+EXVAE_API int exvae_log_normal_standard_fwd(const float* x, int B, int D, float* out, exvae_stream_t stream);
+EXVAE_API int exvae_log_normal_standard_bwd(const float* x, const float* dout, int B, int D, float* dx, exvae_stream_t stream);
+/* log_bernoulli(x, mean, dim=1) (utils/distributions.py:44-51), probs clamped to [1e-5, 1-1e-5] */
+EXVAE_API int exvae_log_bernoulli_fwd(const float* x, const float* mean, int B, int P, float* out, exvae_stream_t stream);
+EXVAE_API int exvae_log_bernoulli_bwd(const float* x, const float* mean, const float* dout, int B, int P, float* dmean,
+                            exvae_stream_t stream);
+/* log_logistic_256(x, mean, logvar, dim=1) (utils/distributions.py:54-66) */
+EXVAE_API int exvae_log_logistic256_fwd(const float* x, const float* mean, const float* logvar, int B, int P, float* out,
+                              exvae_stream_t stream);
+EXVAE_API int exvae_log_logistic256_bwd(const float* x, const float* mean, const float* logvar, const float* dout, int B, int P,
+                              float* dmean, float* dlogvar, exvae_stream_t stream);
+/* loss = mean(-RE + beta*KL), RE.mean, KL.mean (models/BaseModel.py:71-75); out3 = {loss, RE, KL};
+ * average=0 writes per-sample loss into loss_b [B] instead (out3 may be NULL). */
+EXVAE_API int exvae_elbo_reduce(const float* RE, const float* KL, int B, float beta, int average, float* out3, float* loss_b,
+                      exvae_stream_t stream);
+
+/* out[i] = sum_j c[j] * x_j[i] over up to 4 vectors (NULL x_j are skipped): the KL assembly
+ * -(log_p_z1 + log_p_z2 - log_q_z1 - log_q_z2) of models/AbsModel.py:19, models/AbsHModel.py:29. */
+EXVAE_API int exvae_lincomb4(const float* x0, const float* x1, const float* x2, const float* x3, float c0, float c1,
+                             float c2, float c3, int64_t n, float* out, exvae_stream_t stream);
+/* backward of exvae_elbo_reduce: g3 = upstream grads of {loss, RE, KL} (average=1) or g_loss_b [B]
+ * (average=0, g3 ignored); writes dRE [B], dKL [B]. */
+EXVAE_API int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int B, float beta, int average, float* dRE,
+                                    float* dKL, exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
+ * Device-side replacements for torch.bernoulli (utils/training.py:31), torch.randint
+ * (models/BaseModel.py:245,257) and normal_() (models/BaseModel.py:81).  `counter` is a device
+ * uint64 that the kernel reads as the stream offset, so graph replays draw fresh numbers once
+ * exvae_rng_advance has bumped it.                                                            */
+EXVAE_API int exvae_rng_bernoulli(const float* p, int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq, float* out,
+                        exvae_stream_t stream);
+EXVAE_API int exvae_rng_normal(int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq, float* out,
+                     exvae_stream_t stream);
+EXVAE_API int exvae_rng_randint(int64_t low, int64_t high, int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq,
+                      int64_t* out, exvae_stream_t stream);
+EXVAE_API int exvae_rng_advance(uint64_t* counter, uint64_t by, exvae_stream_t stream);
+
+/* ---------------------------------------------------------------- AdamNormGrad (utils/optimizer.py:32-80)
+ * One fused multi-tensor step: per-tensor g / (||g||_2 + 1e-7), Adam moments, bias correction
+ * from the device step counter (incremented by the call), parameter update.
+ * table: device array of n_tensors records {param*, grad*, exp_avg*, exp_avg_sq*, numel} laid out
+ * as 5 x int64 per tensor.  norms: scratch [n_tensors] fp32.  step: device int64[1].            */
+EXVAE_API int exvae_adam_normgrad_step(const int64_t* table, int n_tensors, int64_t max_numel, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int64_t* step, float* norms,
+                             exvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXVAE_B200_H_ */

@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/exvae_b200.h declares, rejects bad arguments without touching a GPU, and the host-side
+mirror keeps the reference's state_dict keys."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from exemplar_vae_b200 import build as B
+    if not os.path.exists(B.LIB):
+        B.build()
+    from exemplar_vae_b200._lib import lib
+    return lib()
+
+
+def test_library_exports_every_declared_symbol(L):
+    from exemplar_vae_b200._lib import LIB_PATH, parse_header
+    protos = parse_header()
+    assert len(protos) >= 40
+    dll = ctypes.CDLL(LIB_PATH)
+    for name in protos:
+        assert hasattr(dll, name), name
+    assert L.exvae_abi_version() == 1
+    assert L.exvae_error_string(0) == b"ok"
+    assert b"workspace" in L.exvae_error_string(-3)
+
+
+def test_argument_errors_without_gpu(L):
+    # null pointers / non-positive sizes are rejected before any CUDA call
+    assert L.exvae_pairwise_distance(None, None, 4, 4, 4, None, None) == -1
+    assert L.exvae_gated_dense_fwd(None, None, None, None, None, 1, 1, 1, None, None, None, None) == -1
+    assert L.exvae_prior_lse_workspace_bytes(0, 10, 40) == 0
+    n = L.exvae_prior_lse_workspace_bytes(512, 25000, 40)
+    assert 4e6 < n < 2e8
+    assert L.exvae_knn_workspace_bytes(100, 25000, 40, 10) >= 100 * 25000 * 4
+    assert L.exvae_gated_dense_bwd_workspace_bytes(25000, 784, 300) > 25000 * 600 * 4
+
+
+def test_header_cites_reference_for_each_group():
+    src = open(os.path.join(ROOT, "include", "exvae_b200.h")).read()
+    for cite in ("utils/distributions.py:12-18", "models/BaseModel.py:98-109", "models/BaseModel.py:263-264",
+                 "utils/nn.py:44-69", "utils/optimizer.py:32-80", "utils/knn_on_latent.py:4-9"):
+        assert cite in src
+
+
+def test_state_dict_keys_match_reference_checkpoint_layout():
+    import exemplar_vae_b200 as E
+    from oracle import exvae_oracle as O
+    for name, n_tensors, n_params in (("vae", 23, 1116865), ("hvae_2level", 55, 2431025)):
+        args = O.make_args(model_name=name)
+        m = E.importing_model(args)(args)
+        sd = m.state_dict()
+        assert len(sd) == n_tensors and sum(v.numel() for v in sd.values()) == n_params
+        ref = O.init_params(args)
+        assert set(sd.keys()) == set(ref.keys())
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    ck = "/root/reference/pretrained_model/exemplar_prior_on_dynamic_mnist_model_name=vae/1/checkpoint_best.pth"
+    if os.path.exists(ck):   # build container only
+        args = O.make_args(model_name="vae")
+        m = E.importing_model(args)(args)
+        m.load_state_dict(torch.load(ck, map_location="cpu")["state_dict"])
+        assert abs(float(m.prior_log_variance.detach()) + 2.4189) < 1e-3
+
+
+def test_product_has_no_cpu_path():
+    import exemplar_vae_b200 as E
+    from oracle import exvae_oracle as O
+    args = O.make_args(model_name="vae", hidden_size=16)
+    m = E.importing_model(args)(args)
+    x = torch.rand(4, 784)
+    with pytest.raises(E.ExvaeError):
+        m.q_z(x)
+
+
+def test_set_beta_schedule():
+    from types import SimpleNamespace
+    import exemplar_vae_b200 as E
+    a = SimpleNamespace(warmup=100)
+    assert E.set_beta(a, 0) == 0.0 and E.set_beta(a, 50) == 0.5 and E.set_beta(a, 500) == 1.0
+    assert E.set_beta(SimpleNamespace(warmup=0), 3) == 1.0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "exemplar_vae_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("against the oracle", ""), fn

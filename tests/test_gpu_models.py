@@ -1,0 +1,186 @@
+"""GPU parity tests of the model-level drop-in (calculate_loss / backward / AdamNormGrad /
+kNN exemplar selection) against the reference-generated goldens and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import exvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rtol, atol=0.0):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a.astype(np.float64), b.astype(np.float64), rtol=rtol, atol=atol)
+
+
+def build(args, g=None):
+    import exemplar_vae_b200 as E
+    model = E.importing_model(args)(args).cuda()
+    if g is not None:
+        sd = {k[2:]: torch.tensor(v) for k, v in g.items() if k.startswith("p:")}
+        model.load_state_dict(sd)
+    return model
+
+
+def _golden_step(g, model_name):
+    import exemplar_vae_b200 as E
+    side = int(g["side"])
+    N = len(g["ex_idx"])
+    args = O.make_args(model_name=model_name, hidden_size=int(g["hidden"]), number_components=N,
+                       training_set_size=int(g["T"]), input_size=[1, side, side], device="cuda")
+    model = build(args, g)
+    model.train()
+    # dataset: only the exemplar rows are known; place them at their dataset positions
+    T = int(g["T"])
+    data = torch.zeros(T, side * side)
+    data[torch.tensor(g["ex_idx"])] = torch.tensor(g["exemplars"])
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    n_eps = 1 if model_name == "vae" else 2
+    x = torch.tensor(g["x"]).cuda(); xi = torch.tensor(g["x_idx"]).cuda()
+    beta = float(g["beta"])
+
+    def override():
+        return {"eps": [torch.tensor(g[f"eps{i}"]).cuda() for i in range(n_eps)],
+                "exemplar_indices": torch.tensor(g["ex_idx"]).cuda()}
+
+    model.rng_override = override()
+    with torch.no_grad():
+        lb, reb, klb = model.calculate_loss((x, xi), beta, average=False, dataset=dataset)
+    close(lb, g["loss_b"], rtol=1e-4); close(reb, g["RE_b"], rtol=1e-4); close(klb, g["KL_b"], rtol=1e-4, atol=1e-3)
+
+    opt = E.AdamNormGrad(model.parameters(), lr=float(g["lr"]))
+    model.rng_override = override()
+    opt.zero_grad()
+    loss, RE, KL = model.calculate_loss((x, xi), beta, average=True, dataset=dataset)
+    close(loss, g["loss"], rtol=1e-4); close(RE, g["RE"], rtol=1e-4); close(KL, g["KL"], rtol=1e-4)
+    loss.backward()
+    for n, p in model.named_parameters():
+        ref = g["g:" + n]
+        scale = np.abs(ref).max() + 1e-12
+        close(p.grad, ref, rtol=2e-3, atol=2e-4 * scale)
+    opt.step()
+    for k, v in model.state_dict().items():
+        close(v, g["n:" + k], rtol=1e-4, atol=2e-6)
+
+
+def test_vae_step_golden(golden):
+    _golden_step(golden("vae_step"), "vae")
+
+
+def test_hvae_step_golden(golden):
+    _golden_step(golden("hvae_step"), "hvae_2level")
+
+
+def test_approximate_prior_golden(golden):
+    g = golden("approx")
+    side = int(g["side"])
+    args = O.make_args(model_name="vae", hidden_size=int(g["hidden"]), input_size=[1, side, side],
+                       approximate_prior=True, approximate_k=int(g["k"]), number_components=len(g["ex_idx"]),
+                       training_set_size=g["data"].shape[0], device="cuda")
+    model = build(args, g)
+    model.train()
+    data = torch.tensor(g["data"])
+    T = data.shape[0]
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    with torch.no_grad():
+        cm, clv = model.cache_z(dataset)
+    close(cm, g["cache_mean"], rtol=1e-4, atol=1e-5)
+    cache = (torch.tensor(g["cache_mean"]).cuda(), torch.tensor(g["cache_logvar"]).cuda())
+    x = torch.tensor(g["x"]).cuda(); xi = torch.tensor(g["x_idx"]).cuda()
+    model.rng_override = {"eps": [torch.tensor(g["eps"]).cuda()], "exemplar_indices": torch.tensor(g["ex_idx"]).cuda()}
+    loss, RE, KL = model.calculate_loss((x, xi), 1.0, average=True, cache=cache, dataset=dataset)
+    close(loss, g["loss"], rtol=1e-4); close(KL, g["KL"], rtol=1e-4)
+    close(cache[0], g["cache_after"], rtol=1e-4, atol=1e-5)
+    # the selected dataset indices are bit-exact
+    model.rng_override = {"eps": [], "exemplar_indices": torch.tensor(g["ex_idx"]).cuda()}
+    cache2 = (torch.tensor(g["cache_mean"]).cuda(), torch.tensor(g["cache_logvar"]).cuda())
+    with torch.no_grad():
+        zm, zl = model.q_z(x)
+        sel = model.get_approximate_nearest_exemplars((zm, zl, xi), cache2, dataset)
+    assert np.array_equal(sel[2].cpu().numpy(), g["sel_indices"])
+    close(sel[0], g["sel_mean"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("model_name,B,N,T,H", [("vae", 100, 1000, 2000, 300), ("hvae_2level", 64, 500, 1000, 300)])
+def test_training_steps_track_oracle(model_name, B, N, T, H):
+    """cfg1-sized (N=1000, B=100) multi-step trajectory: same draws replayed through the oracle."""
+    import exemplar_vae_b200 as E
+    args = O.make_args(model_name=model_name, hidden_size=H, number_components=N, training_set_size=T, device="cuda")
+    p = O.init_params(args, seed=7)
+    model = build(args)
+    model.load_state_dict({k: v.detach().clone() for k, v in p.items()})
+    model.train()
+    data = O.synthetic_dataset(T)
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    opt = E.AdamNormGrad(model.parameters(), lr=5e-4)
+    st = {}
+    gen = torch.Generator().manual_seed(99)
+    for it in range(3):
+        bidx = torch.randperm(T, generator=gen)[:B]
+        x = torch.bernoulli(data[bidx], generator=gen)
+        ex_idx = torch.randint(0, T, (N,), generator=gen)
+        ex_idx[:5] = bidx[:5]
+        D = 40
+        if model_name == "vae":
+            eps = {"eps": torch.randn(B, D, generator=gen)}
+            eps_list = [eps["eps"]]
+        else:
+            eps = {"eps2": torch.randn(B, D, generator=gen), "eps1": torch.randn(B, D, generator=gen)}
+            eps_list = [eps["eps2"], eps["eps1"]]
+        ro = dict(x=x, exemplar_indices=ex_idx, **eps)
+        l_ref, re_ref, kl_ref = O.train_step(p, st, args, data[bidx], bidx.view(-1, 1), data, 0.5, gen, rng_override=ro)
+        model.rng_override = {"eps": [e.cuda() for e in eps_list], "exemplar_indices": ex_idx.cuda()}
+        opt.zero_grad()
+        loss, RE, KL = model.calculate_loss((x.cuda(), bidx.view(-1, 1).cuda()), 0.5, average=True, dataset=dataset)
+        loss.backward()
+        opt.step()
+        close(loss, l_ref, rtol=1e-4); close(RE, re_ref, rtol=1e-4); close(KL, kl_ref, rtol=1e-4)
+    for k, v in model.state_dict().items():
+        close(v, p[k], rtol=1e-3, atol=1e-5)
+
+
+def test_graphed_step_matches_eager_and_device_rng_runs():
+    import exemplar_vae_b200 as E
+    T, B, N = 4000, 128, 1000
+    args = O.make_args(model_name="vae", hidden_size=300, number_components=N, training_set_size=T, device="cuda")
+    data = O.synthetic_dataset(T)
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    model = build(args)
+    opt = E.AdamNormGrad(model.parameters(), lr=5e-4)
+    step = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=2, use_graph=True)
+    losses = []
+    for it in range(5):
+        idx = torch.arange(it * B, (it + 1) * B)
+        out = step.step(data[idx].cuda(), idx.cuda())
+        losses.append(out.clone())
+    losses = torch.stack(losses).cpu()
+    assert torch.isfinite(losses).all()
+    assert losses[:, 0].std() > 0, "replays must draw fresh random numbers"
+    assert 300 < losses[0, 0] < 900
+    assert step.launches_per_step > 20
+    # train_one_epoch API (eager path)
+    loader = torch.utils.data.DataLoader(torch.utils.data.Subset(dataset, range(512)), batch_size=128)
+    loader.dataset.tensors = dataset.tensors
+    args.dynamic_binarization = True
+    l, re, kl = E.train_one_epoch(1, args, loader, model, opt)
+    assert np.isfinite([l, re, kl]).all()
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    import exemplar_vae_b200 as E
+    args = O.make_args(model_name="vae", hidden_size=32, device="cuda")
+    m = build(args)
+    opt = E.AdamNormGrad(m.parameters(), lr=1e-3)
+    for p in m.parameters():
+        p.grad = torch.randn_like(p)
+    opt.step()
+    E.save_model(str(tmp_path / "t.pth"), str(tmp_path / "c.pth"),
+                 {"epoch": 1, "state_dict": m.state_dict(), "optimizer": opt.state_dict(), "best_loss": 1.0, "e": 0})
+    m2 = build(args)
+    opt2 = E.AdamNormGrad(m2.parameters(), lr=1e-3)
+    ck = E.load_model(str(tmp_path / "c.pth"), m2, opt2)
+    assert ck["epoch"] == 1
+    for a, b in zip(m.parameters(), m2.parameters()):
+        assert torch.equal(a, b)
