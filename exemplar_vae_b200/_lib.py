@@ -56,6 +56,7 @@ class _Lib:
                 f"{LIB_PATH} is missing: the CUDA library has not been built. "
                 "Run `python -m exemplar_vae_b200.build` (needs nvcc); there is no CPU fallback.")
         self._dll = ctypes.CDLL(LIB_PATH)
+        self.profile = None
         self.protos = parse_header()
         for name, (restype, argtypes) in self.protos.items():
             try:
@@ -64,9 +65,26 @@ class _Lib:
                 raise ExvaeError(f"{LIB_PATH} does not export {name} declared in include/exvae_b200.h") from e
             fn.restype = restype
             fn.argtypes = argtypes
-            setattr(self, name, fn)
+            setattr(self, name, self._wrap(name, fn) if restype is ctypes.c_int else fn)
         if self.exvae_abi_version() != 1:
             raise ExvaeError("exvae_b200 ABI version mismatch between header and library")
+
+    def _wrap(self, name, fn):
+        """Optional per-entry-point device timing: when ``self.profile`` is a list, every call is
+        bracketed by CUDA events on the current stream (bench.py uses this for the roofline)."""
+        def call(*args):
+            prof = self.profile
+            if prof is None:
+                return fn(*args)
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            prof.append((name, e0, e1))
+            return rc
+        call.__name__ = name
+        return call
 
     def check(self, rc: int, what: str = ""):
         if rc != EXVAE_OK:

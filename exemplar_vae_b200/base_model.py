@@ -70,6 +70,8 @@ class BaseModel(nn.Module, ABC):
         self.rng = DeviceRng(getattr(args, "seed", 0))
         self.rng_override: Optional[dict] = None   # {'eps': [tensors...], 'exemplar_indices': tensor}
         self.bank_group = None                      # torch.distributed group when the bank is range-sharded
+        self.bank_world, self.bank_rank = 1, 0
+        self.grad_sync = None                       # set by distributed.shard_bank: averages the flat gradient buffer
         self._resident_cache = {}
 
         if self.args.prior == 'vampprior':
@@ -178,8 +180,10 @@ class BaseModel(nn.Module, ABC):
             lv = center_log_variance[0, :] if center_log_variance.dim() == 2 else center_log_variance
             masked = (test is False) and (self.args.no_mask is False) and z_indices is not None
             c_total = getattr(exemplars_embedding, "c_total", None)
-            return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None,
-                                 c_total=c_total, group=self.bank_group if c_total is not None else None)
+            if c_total is not None and self.bank_group is not None:     # range-sharded bank (distributed.py)
+                return ops.prior_lse_sharded(z, centers, lv, z_indices if masked else None,
+                                             center_indices if masked else None, c_total, self.bank_group)
+            return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None)
         raise Exception('Wrong name of the prior!')
 
     # ------------------------------------------------------------------ generation helpers
@@ -245,10 +249,16 @@ class BaseModel(nn.Module, ABC):
         return torch.cat(cached_z, dim=0), torch.cat(cached_log_var, dim=0)
 
     def _exemplar_indices(self, device):
+        """N dataset indices drawn with replacement (BaseModel.py:245); with a range-sharded bank
+        this rank draws (or is handed) only its own N/G of them."""
+        from .distributed import shard_range
+        n = self.args.number_components
+        lo, hi = shard_range(n, self.bank_world, self.bank_rank)
         ro = self.rng_override
         if ro is not None and ro.get('exemplar_indices') is not None:
-            return ro['exemplar_indices'].to(device).reshape(-1)
-        return self.rng.randint(0, self.args.training_set_size, self.args.number_components, device)
+            idx = ro['exemplar_indices'].to(device).reshape(-1)
+            return idx[lo:hi] if (self.bank_world > 1 and idx.numel() == n) else idx
+        return self.rng.randint(0, self.args.training_set_size, hi - lo, device)
 
     def get_exemplar_set(self, z_mean, z_log_var, dataset, cache, x_indices):
         """models/BaseModel.py:243-254"""
@@ -257,6 +267,9 @@ class BaseModel(nn.Module, ABC):
             exemplars_indices = self._exemplar_indices(dev)
             exemplars = ops.gather_rows(self.resident(dataset), exemplars_indices)
             exemplars_z, log_variance = self.q_z(exemplars, prior=True)
+            if self.bank_group is not None:
+                from .distributed import ShardedBank
+                return ShardedBank((exemplars_z, log_variance, exemplars_indices), self.args.number_components)
             return (exemplars_z, log_variance, exemplars_indices)
         return self.get_approximate_nearest_exemplars(z=(z_mean, z_log_var, x_indices), dataset=dataset, cache=cache)
 

@@ -340,7 +340,9 @@ struct BwdPlan {
 inline BwdPlan bwd_plan(int R, int K, int ncat, bool need_dcat) {
   BwdPlan b;
   const int tiles = ceil_div(ncat, GM) * ceil_div(K, GN);
-  int S = ceil_div(2 * sm_count(), tiles);
+  // split the R-reduction so that tiles*S fills ONE wave of the 2-CTA/SM residency (never 1.x waves)
+  const int slots = 2 * sm_count();
+  int S = std::max(1, slots / tiles);
   S = std::max(1, std::min(S, ceil_div(R, 4 * GK)));
   b.kchunk = ceil_div(ceil_div(R, S), GK) * GK;
   b.S = ceil_div(R, b.kchunk);

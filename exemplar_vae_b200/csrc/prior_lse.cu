@@ -569,30 +569,51 @@ __global__ void __launch_bounds__(PR_THREADS, 2)
 }
 
 // rows: dz = (sum_tiles dzs_part - zs * rowsum) / sigma ; rowdot = dzs * zs ; rs = rowsum
+// One CTA per row; the 8 warps stride over the column tiles (4 loads in flight each), lanes over d.
 __global__ void __launch_bounds__(256) prior_bwd_rows_kernel(const float* __restrict__ dzs_part,
                                                              const float* __restrict__ rowsum_part,
                                                              const float* __restrict__ zs,
                                                              const float* __restrict__ isig, int ntile, int B, int D,
                                                              int LD, int Bpad, float* __restrict__ dz,
                                                              float* __restrict__ rowdot, float* __restrict__ rs) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
+  extern __shared__ float sh[];  // [8][LD] partial sums + [8] rowsum partials
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
   float r = 0.f;
-  for (int t = lane; t < ntile; t += 32) r += rowsum_part[(size_t)t * Bpad + b];
+  for (int t = tid; t < ntile; t += 256) r += rowsum_part[(size_t)t * Bpad + b];
   r = warp_sum(r);
-  for (int d0 = 0; d0 < D; d0 += 32) {
+  if (lane == 0) sh[8 * LD + warp] = r;
+  for (int d0 = 0; d0 < LD; d0 += 32) {
     const int d = d0 + lane;
-    if (d < D) {
-      float acc = 0.f;
-      for (int t = 0; t < ntile; ++t) acc += dzs_part[((size_t)t * Bpad + b) * LD + d];
-      const float zv = zs[(size_t)b * LD + d];
-      const float dzs = acc - zv * r;
-      dz[(size_t)b * D + d] = dzs * isig[d];
-      rowdot[(size_t)b * LD + d] = dzs * zv;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (d < LD) {
+      const float* base = dzs_part + (size_t)b * LD + d;
+      const size_t ts = (size_t)Bpad * LD;
+      int t = warp;
+      for (; t + 24 < ntile; t += 32) {
+        a0 += base[(size_t)t * ts];
+        a1 += base[(size_t)(t + 8) * ts];
+        a2 += base[(size_t)(t + 16) * ts];
+        a3 += base[(size_t)(t + 24) * ts];
+      }
+      for (; t < ntile; t += 8) a0 += base[(size_t)t * ts];
+      sh[warp * LD + d] = (a0 + a1) + (a2 + a3);
     }
   }
-  if (lane == 0) rs[b] = r;
+  __syncthreads();
+  float rtot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) rtot += sh[8 * LD + w];
+  for (int d = tid; d < D; d += 256) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += sh[w * LD + d];
+    const float zv = zs[(size_t)b * LD + d];
+    const float dzs = acc - zv * rtot;
+    dz[(size_t)b * D + d] = dzs * isig[d];
+    rowdot[(size_t)b * LD + d] = dzs * zv;
+  }
+  if (tid == 0) rs[b] = rtot;
 }
 
 // dlogvar[d] = -0.5 * ( sum_b rs[b] + sum_b rowdot[b,d] + sum_tile coldot_part[tile,d] )
@@ -713,7 +734,7 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
   else
     rc = mask ? launch(prior_lse_bwd_kernel<true, 32>) : launch(prior_lse_bwd_kernel<false, 32>);
   if (rc) return rc;
-  prior_bwd_rows_kernel<<<ceil_div(B, 8), 256, 0, st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, w.ntile, B, D, w.LD,
+  prior_bwd_rows_kernel<<<B, 256, (8 * w.LD + 8) * sizeof(float), st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, w.ntile, B, D, w.LD,
                                                         w.Bpad, dz, w.rowdot, w.rs);
   EXVAE_CUDA(cudaGetLastError());
   prior_bwd_dlogvar_kernel<<<1, 1024, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, w.ntile, D, w.LD, dlogvar);

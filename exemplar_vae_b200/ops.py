@@ -269,7 +269,7 @@ class _GatedDense(torch.autograd.Function):
         R, K = x.shape
         O = Wh.shape[0]
         out = torch.empty((R, O), dtype=torch.float32, device=x.device)
-        need = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, Wh, bh, Wg, bg))
+        need = any(ctx.needs_input_grad)
         h = torch.empty_like(out) if need else None
         s = torch.empty_like(out) if need else None
         L.check(L.exvae_gated_dense_fwd(_p(x), _p(Wh), _p(bh), _p(Wg), _p(bg), R, K, O, _p(out), _p(h), _p(s),
@@ -598,3 +598,77 @@ class _LinComb(torch.autograd.Function):
 def lincomb(coeffs, *xs) -> torch.Tensor:
     """sum_j coeffs[j] * xs[j] for up to four same-shaped tensors (KL assembly)."""
     return _LinComb.apply(tuple(coeffs), *xs)
+
+
+# ======================================================================================
+# K1 over a range-sharded exemplar bank (one process per GPU, SURVEY.md §8e)
+# ======================================================================================
+class _PriorLSESharded(torch.autograd.Function):
+    """Every rank holds B local latents and its own shard of the bank.  Forward: all-gather the
+    latents (+indices), run K1 for ALL rows against the LOCAL shard, all-gather the [B_total,4]
+    partial statistics (the single LSE exchange) and merge.  Backward: all-gather the row grads,
+    run the K1 backward against the local shard (dmu is complete for the shard), reduce-scatter
+    the partial dz back to the row owners."""
+
+    @staticmethod
+    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group):
+        import torch.distributed as dist
+        L = lib()
+        z, mu, logvar = _f32(z, "z"), _f32(mu, "mu"), _f32(logvar, "logvar")
+        G, rank = dist.get_world_size(group), dist.get_rank(group)
+        B, D = z.shape
+        C = mu.shape[0]
+        masked = z_idx is not None and mu_idx is not None
+        z_all = torch.empty((G * B, D), dtype=torch.float32, device=z.device)
+        dist.all_gather_into_tensor(z_all, z, group=group)
+        zi_all = None
+        if masked:
+            z_idx = _i64(z_idx).reshape(-1)
+            mu_idx = _i64(mu_idx).reshape(-1)
+            zi_all = torch.empty((G * B,), dtype=torch.int64, device=z.device)
+            dist.all_gather_into_tensor(zi_all, z_idx, group=group)
+        else:
+            mu_idx = None
+        Bt = G * B
+        ws = _ws(L.exvae_prior_lse_workspace_bytes(Bt, C, D), z.device)
+        stats = torch.empty((Bt, 4), dtype=torch.float32, device=z.device)
+        L.check(L.exvae_prior_lse_fwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(stats),
+                                      _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
+        _count(3)
+        all_stats = torch.empty((G, Bt, 4), dtype=torch.float32, device=z.device)
+        dist.all_gather_into_tensor(all_stats, stats, group=group)
+        log_p = torch.empty((Bt,), dtype=torch.float32, device=z.device)
+        lse2 = torch.empty((Bt,), dtype=torch.float32, device=z.device)
+        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z_all), _p(logvar), Bt, D, int(c_total), _p(log_p),
+                                           _p(lse2), _stream()), "prior_lse_finalize")
+        _count(1)
+        ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws)
+        ctx.meta = (B, Bt, C, D, G, rank, group)
+        return log_p[rank * B:(rank + 1) * B].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        L = lib()
+        z_all, mu, logvar, zi_all, mu_idx, lse2, ws = ctx.saved_tensors
+        B, Bt, C, D, G, rank, group = ctx.meta
+        g = _f32(g, "grad")
+        g_all = torch.empty((Bt,), dtype=torch.float32, device=g.device)
+        dist.all_gather_into_tensor(g_all, g, group=group)
+        dz_all = torch.empty_like(z_all)
+        dmu = torch.empty_like(mu)
+        dlv = torch.empty((D,), dtype=torch.float32, device=g.device)
+        L.check(L.exvae_prior_lse_bwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(lse2),
+                                      _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _stream()),
+                "prior_lse_bwd")
+        _count(3)
+        dz = torch.empty((B, D), dtype=torch.float32, device=g.device)
+        dist.reduce_scatter_tensor(dz, dz_all, op=dist.ReduceOp.SUM, group=group)
+        return dz, dmu, dlv.view_as(logvar), None, None, None, None
+
+
+def prior_lse_sharded(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total: int, group) -> torch.Tensor:
+    """``prior_lse`` for a bank range-sharded over ``group``: returns log p(z_b) for the LOCAL rows.
+    Gradients: dz local (summed over shards), dmu for the local shard, dlogvar = this shard's share
+    (the data-parallel gradient all-reduce completes it, like every other replicated parameter)."""
+    return _PriorLSESharded.apply(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total, group)

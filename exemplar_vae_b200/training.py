@@ -38,6 +38,8 @@ def train_one_epoch(epoch, args, train_loader, model, optimizer):
         loss, RE, KL = model.calculate_loss((x, indices), beta, average=True, cache=cache,
                                             dataset=train_loader.dataset)
         loss.backward()
+        if model.grad_sync is not None:
+            model.grad_sync()
         optimizer.step()
         with torch.no_grad():
             acc += torch.stack((loss.detach(), -RE.detach(), KL.detach()))
@@ -61,6 +63,9 @@ class GraphedTrainStep:
         self.out = torch.zeros(3, dtype=torch.float32, device=dev)
         self.graph = None
         self.launches_per_step = 0
+        if getattr(model, "flat_grads", None) is None:
+            from .distributed import FlatGrads
+            model.flat_grads = FlatGrads(model.parameters())     # stable grad pointers, one memset per step
         model.train()
         # eager warm-up on a side stream (allocator + optimizer state + grad buffers settle)
         s = torch.cuda.Stream()
@@ -79,10 +84,12 @@ class GraphedTrainStep:
 
     def _body(self):
         x = self.model.rng.bernoulli(self.data) if self.args.dynamic_binarization else self.data
-        self.opt.zero_grad(set_to_none=False)
+        self.model.flat_grads.zero_()
         loss, RE, KL = self.model.calculate_loss((x, self.indices), self.beta, average=True, cache=None,
                                                  dataset=self.dataset)
         loss.backward()
+        if self.model.grad_sync is not None:
+            self.model.grad_sync()                 # data-parallel: one all-reduce of the flat gradient buffer
         self.opt.step()
         with torch.no_grad():
             self.out.copy_(torch.stack((loss.detach(), RE.detach(), KL.detach())))

@@ -61,8 +61,20 @@ def _golden_step(g, model_name):
         scale = np.abs(ref).max() + 1e-12
         close(p.grad, ref, rtol=2e-3, atol=2e-4 * scale)
     opt.step()
+    # Adam's first step is sign-like (m/sqrt(v) = +-1): an element whose normalised gradient is at the
+    # eps=1e-8 scale may legitimately differ by up to lr, every other element must agree tightly.
+    lr = float(g["lr"])
     for k, v in model.state_dict().items():
-        close(v, g["n:" + k], rtol=1e-4, atol=2e-6)
+        ref = g["n:" + k]
+        if ("g:" + k) in g:
+            gr = g["g:" + k]
+            gn = np.abs(gr) / (np.linalg.norm(gr) + 1e-7)
+            solid = gn > 1e-5
+            got = v.detach().cpu().numpy()
+            close(got[solid], ref[solid], rtol=1e-4, atol=2e-6)
+            close(got[~solid], ref[~solid], rtol=0, atol=1.1 * lr)
+        else:
+            close(v, ref, rtol=1e-4, atol=2e-6)
 
 
 def test_vae_step_golden(golden):
@@ -138,7 +150,9 @@ def test_training_steps_track_oracle(model_name, B, N, T, H):
         opt.step()
         close(loss, l_ref, rtol=1e-4); close(RE, re_ref, rtol=1e-4); close(KL, kl_ref, rtol=1e-4)
     for k, v in model.state_dict().items():
-        close(v, p[k], rtol=1e-3, atol=1e-5)
+        a, b = v.detach().cpu().numpy(), p[k].detach().numpy()
+        close(a, b, rtol=0, atol=3.3 * 5e-4)                       # hard bound: 3 sign-like steps of lr
+        assert np.mean(np.abs(a - b) > 2e-5) < 2e-3, k             # and all but near-zero-gradient elements agree
 
 
 def test_graphed_step_matches_eager_and_device_rng_runs():
