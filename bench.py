@@ -151,13 +151,28 @@ def workload_config(a, world):
 
 
 # ----------------------------------------------------------------------------------------- GPU
+def _finish(world):
+    """Leave without tearing NCCL down: destroying a process group that has collectives baked into
+    live CUDA graphs can block at exit; everything is synchronised and printed by now."""
+    if world > 1:
+        import torch
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
+
+def _dbg(msg):
+    if os.environ.get("EXVAE_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_gpu(a):
     import torch
     import torch.distributed as dist
     import exemplar_vae_b200 as E
     from exemplar_vae_b200 import ops
     from exemplar_vae_b200._lib import lib
-    from oracle import exvae_oracle as O   # only for make_args/synthetic data helpers and the cpu_baseline leg
+    from exemplar_vae_b200.config import default_args, synthetic_train_set
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,20 +180,23 @@ def run_gpu(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     B, N, T = a.batch, a.exemplars, a.train_size
-    args = O.make_args(model_name=a.model, number_components=N, training_set_size=T, device="cuda", seed=rank)
+    args = default_args(model_name=a.model, number_components=N, training_set_size=T, device="cuda", seed=rank)
     torch.manual_seed(0)
     model = E.importing_model(args)(args).to(dev)
-    data_host = O.synthetic_dataset(T)                       # [T,784] U(0,1), CPU generator seed 1234
-    dataset = torch.utils.data.TensorDataset(data_host, torch.arange(T).view(-1, 1), torch.zeros(T))
+    dataset = synthetic_train_set(T)                         # [T,784] U(0,1), CPU generator seed 1234
+    data_host = dataset.tensors[0]
     opt = E.AdamNormGrad(model.parameters(), lr=5e-4)
     if world > 1:
         from exemplar_vae_b200 import distributed as D
         D.shard_bank(model, opt, dist.group.WORLD)
+    _dbg("model built; capturing step")
     step = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=3, use_graph=not a.no_graph)
+    _dbg("step ready")
 
     gen = torch.Generator().manual_seed(100 + rank)
     n_batches = 8
@@ -197,6 +215,7 @@ def run_gpu(a):
     for w in range(max(a.warmup, 3)):
         step.step(dev_x[w % n_batches], dev_i[w % n_batches])
     barrier()
+    _dbg("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -207,6 +226,7 @@ def run_gpu(a):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    _dbg(f"timed region done {ms_total:.1f} ms")
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -229,29 +249,30 @@ def run_gpu(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world / (t.item() / 1e3)
+    _dbg("e2e done")
     h2d = B * CFG["P"] * 4 + B * 8
     d2h = 3 * 4
 
     # ---- per-entry-point device time (eager, CUDA events on the launch stream) -------------
+    # (every rank runs the same steps: they contain collectives; only rank 0 keeps the timings)
     breakdown, prior_ms = {}, None
-    if rank == 0:
-        L = lib()
-        eager = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=2, use_graph=False)
-        L.profile = []
-        reps = 5
-        for k in range(reps):
-            eager.step(dev_x[k % n_batches], dev_i[k % n_batches])
-        torch.cuda.synchronize()
-        for name, s, e in L.profile:
-            breakdown[name] = breakdown.get(name, 0.0) + s.elapsed_time(e) / reps
-        L.profile = None
-        prior_ms = breakdown.get("exvae_prior_lse_fwd")
+    L = lib()
+    eager = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=2, use_graph=False)
+    L.profile = []
+    reps = 5
+    for k in range(reps):
+        eager.step(dev_x[k % n_batches], dev_i[k % n_batches])
+    torch.cuda.synchronize()
+    for name, s, e in L.profile:
+        breakdown[name] = breakdown.get(name, 0.0) + s.elapsed_time(e) / reps
+    L.profile = None
+    prior_ms = breakdown.get("exvae_prior_lse_fwd")
+    _dbg("profile done")
     if world > 1:
         dist.barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     hbm_peak, bf16_peak, peak_src = measured_peaks()
@@ -301,9 +322,8 @@ def run_gpu(a):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "last_loss_re_kl": last,
     }
     line.update(extra)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _finish(world)
 
 
 def step_gemm_flops(model, rows_batch, rows_bank, B):
