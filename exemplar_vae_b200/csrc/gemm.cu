@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace exvae {
 namespace {
@@ -399,38 +400,172 @@ int dense_bwd_common(const float* x, const float* W0, const float* W1, const flo
   return EXVAE_OK;
 }
 
+// ------------------------------------------------------------------ tensor-core (3xTF32) plumbing
+// forward workspace: [x_split 2*R*K][w_split 2*OC*K]  (OC = 2*O gated, O linear); kept by the caller
+// for the backward so operands are split once per step.
+struct FwdWs {
+  size_t off_x, off_w, bytes;
+};
+inline FwdWs fwd_ws_layout(int R, int K, int OC) {
+  FwdWs f;
+  f.off_x = 0;
+  f.off_w = align_up(sizeof(float) * 2 * (size_t)R * K, 256);
+  f.bytes = f.off_w + align_up(sizeof(float) * 2 * (size_t)OC * K, 256);
+  return f;
+}
+inline bool tc_ok(int R, int K, int OC, const void* x) {
+  return tc_enabled() && tc_dims_ok(K) && tc_dims_ok(OC) && al16(x) && R > 0;
+}
+struct TcBwdPlan {
+  int S, kchunk, S2, rows_per;
+  size_t off_dcat, off_dsplit, off_x, off_w, off_part, off_cs, bytes;
+};
+inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
+  TcBwdPlan b;
+  const int tiles = ceil_div(ncat, 128) * ceil_div(K, 128);
+  int S = std::max(1, sm_count() / tiles);
+  S = std::max(1, std::min(S, ceil_div(R, 128)));
+  b.kchunk = ceil_div(ceil_div(R, S), 32) * 32;
+  b.S = ceil_div(R, b.kchunk);
+  b.S2 = std::max(1, std::min(64, ceil_div(R, 256)));
+  b.rows_per = ceil_div(R, b.S2);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  b.off_dcat = take(sizeof(float) * (size_t)R * ncat);
+  b.off_dsplit = take(sizeof(float) * 2 * (size_t)R * ncat);
+  b.off_x = take(sizeof(float) * 2 * (size_t)R * K);
+  b.off_w = take(sizeof(float) * 2 * (size_t)ncat * K);
+  b.off_part = take(sizeof(float) * (size_t)b.S * ncat * K);
+  b.off_cs = take(sizeof(float) * (size_t)b.S2 * ncat);
+  b.bytes = off;
+  return b;
+}
+
+// split x [R,K] and the (one or two segment) weights [OC,K] into hi/lo planes
+int tc_stage_operands(const float* x, const float* W0, const float* W1, int R, int K, int O, float* xs, float* wsplit,
+                      cudaStream_t st) {
+  int rc = tc_split(x, (size_t)R * K, xs, (size_t)R * K, st);
+  if (rc) return rc;
+  const int OC = W1 ? 2 * O : O;
+  rc = tc_split(W0, (size_t)O * K, wsplit, (size_t)OC * K, st);
+  if (rc) return rc;
+  if (W1) rc = tc_split(W1, (size_t)O * K, wsplit + (size_t)O * K, (size_t)OC * K, st);
+  return rc;
+}
+
+// dx / dW / db on the tensor cores.  dcat [R,ncat] fp32 is the pre-activation gradient.
+int dense_bwd_tc(const float* x, const float* W0, const float* W1, const float* dcat, int R, int K, int ncat, int oseg,
+                 float* dx, float* dW0, float* dW1, float* db0, float* db1, const float* xs_in, const float* ws_in,
+                 const TcBwdPlan& plan, char* ws, cudaStream_t st) {
+  float* dsplit = reinterpret_cast<float*>(ws + plan.off_dsplit);
+  int rc = tc_split(dcat, (size_t)R * ncat, dsplit, (size_t)R * ncat, st);
+  if (rc) return rc;
+  const float* xs = xs_in;
+  const float* wsp = ws_in;
+  if (!xs) {
+    float* xs_own = reinterpret_cast<float*>(ws + plan.off_x);
+    float* w_own = reinterpret_cast<float*>(ws + plan.off_w);
+    rc = tc_stage_operands(x, W0, W1, R, K, W1 ? oseg : ncat, xs_own, w_own, st);
+    if (rc) return rc;
+    xs = xs_own;
+    wsp = w_own;
+  }
+  if (dx) {  // dx[R,K] = dcat[R,ncat] . Wcat[ncat,K]  : A K-major, B MN-major (planes [ncat rows][K cols])
+    TcGemm g{};
+    g.a_split = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = false;
+    g.b_split = wsp; g.b_rows = ncat; g.b_cols = K; g.b_mn = true;
+    g.M = R; g.N = K; g.K = ncat; g.epi = TC_PLAIN; g.out0 = dx; g.ldc = K;
+    rc = tc_gemm_launch(g, st);
+    if (rc) return rc;
+  }
+  {  // dWcat[ncat,K] = dcat^T . x : A MN-major (planes [R rows][ncat cols]), B MN-major (planes [R rows][K cols])
+    float* part = reinterpret_cast<float*>(ws + plan.off_part);
+    TcGemm g{};
+    g.a_split = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = true;
+    g.b_split = xs; g.b_rows = R; g.b_cols = K; g.b_mn = true;
+    g.M = ncat; g.N = K; g.K = R; g.epi = TC_SPLITK; g.out0 = part; g.ldc = K;
+    g.splits = plan.S; g.kchunk = plan.kchunk;
+    rc = tc_gemm_launch(g, st);
+    if (rc) return rc;
+    splitk_reduce_kernel<<<ew_blocks((long long)ncat * K), 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0,
+                                                                         dW1 ? dW1 : dW0);
+    EXVAE_CUDA(cudaGetLastError());
+  }
+  if (db0 || db1) {
+    float* cs = reinterpret_cast<float*>(ws + plan.off_cs);
+    dim3 g1(ceil_div(ncat, 32), plan.S2);
+    colsum_partial_kernel<<<g1, 256, 0, st>>>(dcat, R, ncat, plan.rows_per, cs);
+    EXVAE_CUDA(cudaGetLastError());
+    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1);
+    EXVAE_CUDA(cudaGetLastError());
+  }
+  return EXVAE_OK;
+}
+
 }  // namespace
 }  // namespace exvae
 
 using namespace exvae;
 
+extern "C" size_t exvae_dense_fwd_workspace_bytes(int R, int K, int O, int gated) {
+  if (R <= 0 || K <= 0 || O <= 0) return 0;
+  return fwd_ws_layout(R, K, gated ? 2 * O : O).bytes;
+}
+
 extern "C" int exvae_gated_dense_fwd(const float* x, const float* Wh, const float* bh, const float* Wg, const float* bg,
-                                     int R, int K, int O, float* out, float* h_lin, float* sig,
-                                     exvae_stream_t stream) {
+                                     int R, int K, int O, float* out, float* h_lin, float* sig, void* ws,
+                                     size_t ws_bytes, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && Wh && Wg && out && R > 0 && K > 0 && O > 0);
+  cudaStream_t st = as_stream(stream);
+  const FwdWs f = fwd_ws_layout(R, K, 2 * O);
+  if (ws && ws_bytes >= f.bytes && tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws)) {
+    float* xs = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_x);
+    float* wsp = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_w);
+    int rc = tc_stage_operands(x, Wh, Wg, R, K, O, xs, wsp, st);
+    if (rc) return rc;
+    TcGemm g{};
+    g.a_split = xs; g.a_rows = R; g.a_cols = K; g.a_mn = false;
+    g.b_split = wsp; g.b_rows = 2 * O; g.b_cols = K; g.b_mn = false;
+    g.M = R; g.N = O; g.K = K; g.epi = TC_GATED; g.gated_O = O;
+    g.bias0 = bh; g.bias1 = bg; g.out0 = out; g.out1 = h_lin; g.out2 = sig; g.ldc = O;
+    return tc_gemm_launch(g, st);
+  }
   GemmP p{};
   p.A = x; p.lda = K; p.B0 = Wh; p.B1 = Wg; p.ldb = K; p.M = R; p.N = 2 * O; p.K = K; p.kchunk = K;
   p.bias0 = bh; p.bias1 = bg; p.out0 = out; p.out1 = h_lin; p.out2 = sig; p.ldc = O; p.O = O;
   p.a_vec = (K % 4 == 0) && al16(x);
   p.b_vec = (K % 4 == 0) && al16(Wh) && al16(Wg);
   p.c_vec = (O % 4 == 0) && al16(out) && (!h_lin || al16(h_lin)) && (!sig || al16(sig));
-  return launch_gemm<L_KC, L_KC, EPI_GATED>(p, 1, as_stream(stream));
+  return launch_gemm<L_KC, L_KC, EPI_GATED>(p, 1, st);
 }
 
 extern "C" size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O) {
   if (R <= 0 || K <= 0 || O <= 0) return 0;
-  return bwd_plan(R, K, 2 * O, true).bytes;
+  return std::max(bwd_plan(R, K, 2 * O, true).bytes, tc_bwd_plan(R, K, 2 * O).bytes);
 }
 
 extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin,
                                      const float* sig, const float* dout, int R, int K, int O, float* dx, float* dWh,
-                                     float* dbh, float* dWg, float* dbg, void* ws, size_t ws_bytes,
-                                     exvae_stream_t stream) {
+                                     float* dbh, float* dWg, float* dbg, const void* fwd_ws, size_t fwd_ws_bytes,
+                                     void* ws, size_t ws_bytes, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && Wh && Wg && h_lin && sig && dout && dWh && dWg && ws && R > 0 && K > 0 && O > 0);
-  const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
-  if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
+  const bool tc = tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws);
+  if (tc) {
+    const TcBwdPlan plan = tc_bwd_plan(R, K, 2 * O);
+    if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
+    float* dcat = reinterpret_cast<float*>(w + plan.off_dcat);
+    gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, h_lin, sig, R, O, dcat);
+    EXVAE_CUDA(cudaGetLastError());
+    const FwdWs f = fwd_ws_layout(R, K, 2 * O);
+    const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
+    const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
+    const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
+    return dense_bwd_tc(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, xs, wsp, plan, w, st);
+  }
+  const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
+  if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
   float* dcat = reinterpret_cast<float*>(w + plan.off_dcat);
   gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, h_lin, sig, R, O, dcat);
   EXVAE_CUDA(cudaGetLastError());
@@ -438,32 +573,63 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
 }
 
 extern "C" int exvae_linear_fwd(const float* x, const float* W, const float* b, int R, int K, int O, int act, float lo,
-                                float hi, float* out, exvae_stream_t stream) {
+                                float hi, float* out, void* ws, size_t ws_bytes, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && W && out && R > 0 && K > 0 && O > 0);
   EXVAE_CHECK_ARG(act >= EXVAE_ACT_NONE && act <= EXVAE_ACT_RELU);
+  cudaStream_t st = as_stream(stream);
+  const FwdWs f = fwd_ws_layout(R, K, O);
+  if (ws && ws_bytes >= f.bytes && tc_ok(R, K, O, x) && al16(W) && al16(ws)) {
+    float* xs = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_x);
+    float* wsp = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_w);
+    int rc = tc_stage_operands(x, W, nullptr, R, K, O, xs, wsp, st);
+    if (rc) return rc;
+    TcGemm g{};
+    g.a_split = xs; g.a_rows = R; g.a_cols = K; g.a_mn = false;
+    g.b_split = wsp; g.b_rows = O; g.b_cols = K; g.b_mn = false;
+    g.M = R; g.N = O; g.K = K; g.epi = TC_BIAS_ACT;
+    g.bias0 = b; g.out0 = out; g.ldc = O; g.act = act; g.lo = lo; g.hi = hi;
+    return tc_gemm_launch(g, st);
+  }
   GemmP p{};
   p.A = x; p.lda = K; p.B0 = W; p.B1 = W; p.ldb = K; p.M = R; p.N = O; p.K = K; p.kchunk = K;
   p.bias0 = b; p.out0 = out; p.ldc = O; p.act = act; p.lo = lo; p.hi = hi;
   p.a_vec = (K % 4 == 0) && al16(x);
   p.b_vec = (K % 4 == 0) && al16(W);
   p.c_vec = (O % 4 == 0) && al16(out);
-  return launch_gemm<L_KC, L_KC, EPI_BIAS_ACT>(p, 1, as_stream(stream));
+  return launch_gemm<L_KC, L_KC, EPI_BIAS_ACT>(p, 1, st);
 }
 
 extern "C" size_t exvae_linear_bwd_workspace_bytes(int R, int K, int O) {
   if (R <= 0 || K <= 0 || O <= 0) return 0;
-  return bwd_plan(R, K, O, true).bytes;
+  return std::max(bwd_plan(R, K, O, true).bytes, tc_bwd_plan(R, K, O).bytes);
 }
 
 extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out, const float* dout, int R, int K, int O,
-                                int act, float lo, float hi, float* dx, float* dW, float* db, void* ws, size_t ws_bytes,
-                                exvae_stream_t stream) {
+                                int act, float lo, float hi, float* dx, float* dW, float* db, const void* fwd_ws,
+                                size_t fwd_ws_bytes, void* ws, size_t ws_bytes, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && W && dout && dW && ws && R > 0 && K > 0 && O > 0);
   EXVAE_CHECK_ARG(act == EXVAE_ACT_NONE || out != nullptr);
-  const BwdPlan plan = bwd_plan(R, K, O, true);
-  if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
+  const bool tc = tc_ok(R, K, O, x) && al16(W) && al16(ws) && al16(dout);
+  if (tc) {
+    const TcBwdPlan plan = tc_bwd_plan(R, K, O);
+    if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
+    const float* dpre = dout;
+    if (act != EXVAE_ACT_NONE) {
+      float* buf = reinterpret_cast<float*>(w + plan.off_dcat);
+      act_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, out, (long long)R * O, act, lo, hi, buf);
+      EXVAE_CUDA(cudaGetLastError());
+      dpre = buf;
+    }
+    const FwdWs f = fwd_ws_layout(R, K, O);
+    const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
+    const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
+    const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
+    return dense_bwd_tc(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, xs, wsp, plan, w, st);
+  }
+  const BwdPlan plan = bwd_plan(R, K, O, true);
+  if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
   const float* dpre = dout;
   if (act != EXVAE_ACT_NONE) {
     float* buf = reinterpret_cast<float*>(w + plan.off_dcat);
@@ -473,3 +639,5 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
   }
   return dense_bwd_common(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, plan, w, st);
 }
+
+extern "C" int exvae_gemm_backend(void) { return tc_enabled() ? 1 : 0; }

@@ -23,6 +23,11 @@ __all__ = [
 _LAUNCHES = 0  # number of exvae kernels enqueued through this module (bench.py reports it)
 
 
+def gemm_backend() -> str:
+    """'tcgen05-3xtf32' when the tensor-core GEMM is active on the current device, else 'fp32-fma'."""
+    return "tcgen05-3xtf32" if lib().exvae_gemm_backend() == 1 else "fp32-fma"
+
+
 def launch_count() -> int:
     return _LAUNCHES
 
@@ -272,17 +277,19 @@ class _GatedDense(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         h = torch.empty_like(out) if need else None
         s = torch.empty_like(out) if need else None
+        # forward workspace = hi/lo operand splits of the tensor-core backend; kept for the backward
+        fws = _ws(L.exvae_dense_fwd_workspace_bytes(R, K, O, 1), x.device)
         L.check(L.exvae_gated_dense_fwd(_p(x), _p(Wh), _p(bh), _p(Wg), _p(bg), R, K, O, _p(out), _p(h), _p(s),
-                                        _stream()), "gated_dense_fwd")
-        _count(1)
-        ctx.save_for_backward(x, Wh, Wg, h, s)
+                                        _p(fws), fws.numel(), _stream()), "gated_dense_fwd")
+        _count(4)
+        ctx.save_for_backward(x, Wh, Wg, h, s, fws if need else None)
         ctx.has_bias = (bh is not None, bg is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = lib()
-        x, Wh, Wg, h, s = ctx.saved_tensors
+        x, Wh, Wg, h, s, fws = ctx.saved_tensors
         dout = _f32(dout)
         R, K = x.shape
         O = Wh.shape[0]
@@ -292,8 +299,9 @@ class _GatedDense(torch.autograd.Function):
         dbg = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[1] else None
         ws = _ws(L.exvae_gated_dense_bwd_workspace_bytes(R, K, O), x.device)
         L.check(L.exvae_gated_dense_bwd(_p(x), _p(Wh), _p(Wg), _p(h), _p(s), _p(dout), R, K, O, _p(dx), _p(dWh),
-                                        _p(dbh), _p(dWg), _p(dbg), _p(ws), ws.numel(), _stream()), "gated_dense_bwd")
-        _count(5 + (1 if dx is not None else 0))
+                                        _p(dbh), _p(dWg), _p(dbg), _p(fws), fws.numel() if fws is not None else 0,
+                                        _p(ws), ws.numel(), _stream()), "gated_dense_bwd")
+        _count(6 + (1 if dx is not None else 0))
         return dx, dWh, dbh, dWg, dbg
 
 
@@ -311,16 +319,18 @@ class _Linear(torch.autograd.Function):
         R, K = x.shape
         O = W.shape[0]
         out = torch.empty((R, O), dtype=torch.float32, device=x.device)
-        L.check(L.exvae_linear_fwd(_p(x), _p(W), _p(b), R, K, O, act, lo, hi, _p(out), _stream()), "linear_fwd")
-        _count(1)
-        ctx.save_for_backward(x, W, out if act != ACT_NONE else None)
+        fws = _ws(L.exvae_dense_fwd_workspace_bytes(R, K, O, 0), x.device)
+        L.check(L.exvae_linear_fwd(_p(x), _p(W), _p(b), R, K, O, act, lo, hi, _p(out), _p(fws), fws.numel(),
+                                   _stream()), "linear_fwd")
+        _count(3)
+        ctx.save_for_backward(x, W, out if act != ACT_NONE else None, fws if any(ctx.needs_input_grad) else None)
         ctx.cfg = (act, lo, hi, b is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = lib()
-        x, W, out = ctx.saved_tensors
+        x, W, out, fws = ctx.saved_tensors
         act, lo, hi, has_b = ctx.cfg
         dout = _f32(dout)
         R, K = x.shape
@@ -330,8 +340,9 @@ class _Linear(torch.autograd.Function):
         db = torch.empty((O,), dtype=torch.float32, device=x.device) if has_b else None
         ws = _ws(L.exvae_linear_bwd_workspace_bytes(R, K, O), x.device)
         L.check(L.exvae_linear_bwd(_p(x), _p(W), _p(out), _p(dout), R, K, O, act, lo, hi, _p(dx), _p(dW), _p(db),
-                                   _p(ws), ws.numel(), _stream()), "linear_bwd")
-        _count(4 + (1 if dx is not None else 0) + (1 if act != ACT_NONE else 0))
+                                   _p(fws), fws.numel() if fws is not None else 0, _p(ws), ws.numel(), _stream()),
+                "linear_bwd")
+        _count(5 + (1 if dx is not None else 0) + (1 if act != ACT_NONE else 0))
         return dx, dW, db, None, None, None
 
 

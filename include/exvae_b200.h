@@ -123,22 +123,32 @@ EXVAE_API int exvae_scatter_rows(float* dst, const int64_t* idx, int n_rows, int
 
 /* ---------------------------------------------------------------- dense layers (K3)
  * GatedDense (utils/nn.py:44-69): out = (x Wh^T + bh) * sigmoid(x Wg^T + bg).
- * x [R,K], Wh/Wg [O,K], out [R,O].  h_lin/sig [R,O] are saved for the backward (NULL to skip).   */
+ * x [R,K], Wh/Wg [O,K], out [R,O].  h_lin/sig [R,O] are saved for the backward (NULL to skip).
+ *
+ * Backend: error-compensated 3xTF32 on the tcgen05 tensor cores when the shapes allow TMA (K and
+ * the output width multiples of 4, 16-byte aligned pointers) and a forward workspace is given,
+ * else the fp32 FMA-pipe GEMM (EXVAE_GEMM=simt forces the latter).  The forward workspace holds
+ * the hi/lo operand splits; pass it to the backward (fwd_ws) to reuse them, or NULL.               */
+EXVAE_API size_t exvae_dense_fwd_workspace_bytes(int R, int K, int O, int gated);
 EXVAE_API int exvae_gated_dense_fwd(const float* x, const float* Wh, const float* bh, const float* Wg, const float* bg, int R,
-                          int K, int O, float* out, float* h_lin, float* sig, exvae_stream_t stream);
+                          int K, int O, float* out, float* h_lin, float* sig, void* ws, size_t ws_bytes,
+                          exvae_stream_t stream);
 EXVAE_API size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O);
 /* dx may be NULL (first layer: the input is data). */
 EXVAE_API int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin, const float* sig,
                           const float* dout, int R, int K, int O, float* dx, float* dWh, float* dbh, float* dWg,
-                          float* dbg, void* ws, size_t ws_bytes, exvae_stream_t stream);
+                          float* dbg, const void* fwd_ws, size_t fwd_ws_bytes, void* ws, size_t ws_bytes,
+                          exvae_stream_t stream);
 /* nn.Linear / NonLinear (utils/nn.py:29-41): out = act(x W^T + b); b may be NULL. */
 EXVAE_API int exvae_linear_fwd(const float* x, const float* W, const float* b, int R, int K, int O, int act, float lo, float hi,
-                     float* out, exvae_stream_t stream);
+                     float* out, void* ws, size_t ws_bytes, exvae_stream_t stream);
 EXVAE_API size_t exvae_linear_bwd_workspace_bytes(int R, int K, int O);
 /* `out` is the forward OUTPUT (post activation); dx / db may be NULL. */
 EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out, const float* dout, int R, int K, int O, int act,
-                     float lo, float hi, float* dx, float* dW, float* db, void* ws, size_t ws_bytes,
-                     exvae_stream_t stream);
+                     float lo, float hi, float* dx, float* dW, float* db, const void* fwd_ws, size_t fwd_ws_bytes,
+                     void* ws, size_t ws_bytes, exvae_stream_t stream);
+/* 1 = tcgen05 3xTF32 backend active on the current device, 0 = fp32 FMA-pipe backend */
+EXVAE_API int exvae_gemm_backend(void);
 
 /* ---------------------------------------------------------------- element-wise pieces
  * reparameterize (models/BaseModel.py:79-82): z = mu + exp(0.5 logvar) * eps (eps injected). */
