@@ -424,6 +424,9 @@ inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   TcBwdPlan b;
   const int tiles = ceil_div(ncat, 128) * ceil_div(K, 128);
   int S = std::max(1, sm_count() / tiles);
+  // accuracy: the TMEM accumulator is fp32 with truncating adds, so cap the length of one accumulation
+  // chain at 2048 rows and let the fp32 split-K reduction (round-to-nearest) combine the chunks
+  S = std::max(S, ceil_div(R, 2048));
   S = std::max(1, std::min(S, ceil_div(R, 128)));
   b.kchunk = ceil_div(ceil_div(R, S), 32) * 32;
   b.S = ceil_div(R, b.kchunk);

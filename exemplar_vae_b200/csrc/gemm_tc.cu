@@ -83,9 +83,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only swizzle the
+//   tensor core accepts for MN-major 32-bit operands; TMA counterpart: SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=tf32, majors, N>>3, M>>4
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn) {
@@ -179,14 +181,15 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         const uint32_t sb_lo = sb_hi + B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TBK / 8; ++ks) {
-          // K-major: advance 8 tf32 = 32 bytes inside the swizzled 128-byte row; LBO unused, SBO = 8 rows
-          // MN-major: advance 8 k-rows = 1024 bytes; LBO = next 32-wide MN chunk (4096), SBO = 8 k-rows
+          // K-major : advance 8 tf32 = 32 bytes inside the swizzled 128-byte row; LBO unused, SBO = 8 rows (1024 B)
+          // MN-major: advance 8 k-rows = 1024 bytes; LBO = next 32-wide MN chunk (4096 B), SBO = next group of
+          //           4 k-rows (512 B) of the 32-byte-atom swizzle
           const uint32_t aoff = A_MN ? ks * 1024 : ks * 32;
           const uint32_t boff = B_MN ? ks * 1024 : ks * 32;
-          const uint64_t a_hi = umma_desc(sa_hi + aoff, A_MN ? 4096 : 16, 1024);
-          const uint64_t a_lo = umma_desc(sa_lo + aoff, A_MN ? 4096 : 16, 1024);
-          const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, 1024);
-          const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, 1024);
+          const uint64_t a_hi = umma_desc(sa_hi + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+          const uint64_t a_lo = umma_desc(sa_lo + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+          const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
+          const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
           umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
           umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
           umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
@@ -349,7 +352,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // 3-D map over split planes [2][rows][cols] (cols contiguous), box {32, box_rows, 1}, SWIZZLE_128B.
-int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_rows, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return EXVAE_ERR_UNSUPPORTED;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
@@ -357,7 +360,9 @@ int make_map(CUtensorMap* map, const float* base, int rows, int cols, int box_ro
   cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EXVAE_OK : EXVAE_ERR_UNSUPPORTED;
 }
@@ -412,10 +417,10 @@ int tc_split(const float* x, size_t n, float* out, size_t plane_stride, cudaStre
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   constexpr int BN = 128;
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, g.a_split, g.a_rows, g.a_cols, g.a_mn ? 32 : TBM);
+  int rc = make_map(&ma, g.a_split, g.a_rows, g.a_cols, g.a_mn ? 32 : TBM, g.a_mn);
   if (rc) return rc;
   const int b_box = g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN);
-  rc = make_map(&mb, g.b_split, g.b_rows, g.b_cols, b_box);
+  rc = make_map(&mb, g.b_split, g.b_rows, g.b_cols, b_box, g.b_mn);
   if (rc) return rc;
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;

@@ -227,7 +227,7 @@ def test_gated_dense_fwd_bwd(ops, R, K, Oo):
     ref.backward(dout.double())
     cs = [t.cuda().requires_grad_(True) for t in (x, Wh, bh, Wg, bg)]
     out = ops.gated_dense(*cs)
-    close(out, ref, rtol=1e-5, atol=1e-5)
+    close(out, ref, rtol=2e-5, atol=3e-5)      # 3xTF32 tensor-core path: ~5e-6 of the output scale
     out.backward(dout.cuda())
     for c, t in zip(cs, ts):
         close(c.grad, t.grad, rtol=1e-4, atol=1e-4)
@@ -248,13 +248,13 @@ def test_linear_fwd_bwd(ops, act, R, K, Oo):
     ref = fn(pre); ref.backward(dout.double())
     cs = [t.cuda().requires_grad_(True) for t in (x, W, b)]
     out = ops.linear(cs[0], cs[1], cs[2], code, -0.5, 0.7)
-    close(out, ref, rtol=1e-5, atol=1e-5)
+    close(out, ref, rtol=2e-5, atol=3e-5)
     out.backward(dout.cuda())
     for c, t in zip(cs, ts):
         close(c.grad, t.grad, rtol=1e-4, atol=1e-4)
     # no bias / no input grad variant
     out2 = ops.linear(x.cuda(), cs[1], None, code, -0.5, 0.7)
-    close(out2, fn(ts[0] @ ts[1].t()), rtol=1e-5, atol=1e-5)
+    close(out2, fn(ts[0] @ ts[1].t()), rtol=2e-5, atol=3e-5)
 
 
 # ------------------------------------------------------------------ element-wise
