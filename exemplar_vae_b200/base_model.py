@@ -72,6 +72,7 @@ class BaseModel(nn.Module, ABC):
         self.bank_group = None                      # torch.distributed group when the bank is range-sharded
         self.bank_world, self.bank_rank = 1, 0
         self.grad_sync = None                       # set by distributed.shard_bank: averages the flat gradient buffer
+        self.fuse_exemplar_encoder = True           # encode batch + exemplars in ONE pass of the shared trunk
         self._resident_cache = {}
 
         if self.args.prior == 'vampprior':
@@ -135,7 +136,13 @@ class BaseModel(nn.Module, ABC):
     def calculate_loss(self, x, beta=1., average=False, exemplars_embedding=None, cache=None, dataset=None):
         """models/BaseModel.py:65-77 — returns (loss, RE, KL): scalars if ``average`` else [B]."""
         x, x_indices = x
-        x_mean, x_logvar, latent_stats = self.forward(x)
+        zq = None
+        if (self.fuse_exemplar_encoder and exemplars_embedding is None and dataset is not None
+                and self.args.prior == 'exemplar_prior' and self.args.approximate_prior is False):
+            # B200-first: the reference encodes the batch (q_z(x)) and the N exemplars (q_z(.., prior=True))
+            # in two passes of the same trunk; here they share one GEMM chain over B+N rows.
+            zq, exemplars_embedding = self.q_z_with_exemplars(x, dataset)
+        x_mean, x_logvar, latent_stats = self.forward(x, zq=zq)
         RE = self.reconstruction_loss(x.reshape(x_mean.shape), x_mean, x_logvar)
         KL = self.kl_loss(latent_stats, exemplars_embedding, dataset, cache, x_indices)
         if average:
@@ -237,6 +244,32 @@ class BaseModel(nn.Module, ABC):
             z_q_logvar = self.q_z_logvar(h)
         return z_q_mean.reshape(-1, self.args.z1_size), z_q_logvar.reshape(-1, self.args.z1_size)
 
+    def q_z_with_exemplars(self, x, dataset):
+        """(q_z(x), get_exemplar_set(...)) of models/BaseModel.py:205-221,243-248 computed together:
+        exemplar rows are gathered straight behind the batch rows and the encoder trunk runs once."""
+        dev = x.device
+        B = x.shape[0]
+        P = int(np.prod(self.args.input_size))
+        exemplars_indices = self._exemplar_indices(dev)
+        n = exemplars_indices.numel()
+        rows = torch.empty((B + n, P), dtype=torch.float32, device=dev)
+        rows[:B].copy_(x.reshape(B, P))
+        ops.gather_rows(self.resident(dataset), exemplars_indices, out=rows[B:])
+        xin = rows
+        if 'conv' in self.args.model_name:
+            xin = rows.view(-1, self.args.input_size[0], self.args.input_size[1], self.args.input_size[2])
+        h = self.q_z_layers(xin)
+        if self.args.model_name == 'convhvae_2level':
+            h = h.view(B + n, -1)
+        mean_all = self.q_z_mean(h).reshape(B + n, -1)
+        z_q_logvar = self.q_z_logvar(h[:B]).reshape(B, -1)
+        ex_logvar = self.prior_log_variance.expand(n, self.args.z1_size)
+        exemplar_set = (mean_all[B:], ex_logvar, exemplars_indices)
+        if self.bank_group is not None:
+            from .distributed import ShardedBank
+            exemplar_set = ShardedBank(exemplar_set, self.args.number_components)
+        return (mean_all[:B], z_q_logvar), exemplar_set
+
     def cache_z(self, dataset, prior=True, cuda=True):
         """models/BaseModel.py:223-241 — embed the whole (resident) dataset in chunks of 10 000."""
         data = self.resident(dataset)
@@ -325,8 +358,8 @@ class AbsModel(BaseModel):
             x_logvar = self.decoder_logstd * x_mean.new_ones(size=x_mean.shape)
         return x_mean.reshape(-1, P), x_logvar.reshape(-1, P)
 
-    def forward(self, x, label=0, num_categories=10):
-        z_q_mean, z_q_logvar = self.q_z(x)
+    def forward(self, x, label=0, num_categories=10, zq=None):
+        z_q_mean, z_q_logvar = self.q_z(x) if zq is None else zq
         z_q = self.reparameterize(z_q_mean, z_q_logvar)
         x_mean, x_logvar = self.p_x(z_q)
         return x_mean, x_logvar, (z_q, z_q_mean, z_q_logvar)
@@ -386,8 +419,8 @@ class BaseHModel(BaseModel):
                 x_logvar = x_logvar.view(-1, P)
         return x_mean, x_logvar
 
-    def forward(self, x):
-        z2_q_mean, z2_q_logvar = self.q_z(x)
+    def forward(self, x, zq=None):
+        z2_q_mean, z2_q_logvar = self.q_z(x) if zq is None else zq
         z2_q = self.reparameterize(z2_q_mean, z2_q_logvar, sub=0)
         z1_q_mean, z1_q_logvar = self.q_z1(x, z2_q)
         z1_q = self.reparameterize(z1_q_mean, z1_q_logvar, sub=1)

@@ -251,14 +251,15 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmP p) {
 
 // out rows m < mseg -> out0[m], else out1[m - mseg]
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S, int M, int N, int mseg,
-                                                            float* __restrict__ out0, float* __restrict__ out1) {
+                                                            float* __restrict__ out0, float* __restrict__ out1,
+                                                            int accumulate) {
   const size_t total = (size_t)M * N;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     float a = 0.f;
     for (int s = 0; s < S; ++s) a += part[(size_t)s * total + e];
     const int m = (int)(e / N);
-    if (m < mseg) out0[e] = a;
-    else out1[e - (size_t)mseg * N] = a;
+    float* dst = m < mseg ? out0 + e : out1 + (e - (size_t)mseg * N);
+    *dst = accumulate ? *dst + a : a;
   }
 }
 
@@ -282,16 +283,14 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
 }
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int S, int ncols, int seg,
-                                                           float* __restrict__ out0, float* __restrict__ out1) {
+                                                           float* __restrict__ out0, float* __restrict__ out1,
+                                                           int accumulate) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
   float a = 0.f;
   for (int s = 0; s < S; ++s) a += part[(size_t)s * ncols + col];
-  if (col < seg) {
-    if (out0) out0[col] = a;
-  } else if (out1) {
-    out1[col - seg] = a;
-  }
+  float* dst = col < seg ? (out0 ? out0 + col : nullptr) : (out1 ? out1 + (col - seg) : nullptr);
+  if (dst) *dst = accumulate ? *dst + a : a;
 }
 
 // dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*h*sig*(1-sig)      (d/dh and d/dg of h*sigmoid(g))
@@ -363,7 +362,7 @@ inline BwdPlan bwd_plan(int R, int K, int ncat, bool need_dcat) {
 // shared tail of both backward passes: dx, dW (split-K over rows + reduce), db
 int dense_bwd_common(const float* x, const float* W0, const float* W1, const float* dcat, int R, int K, int ncat, int oseg,
                      float* dx, float* dW0, float* dW1, float* db0, float* db1, const BwdPlan& plan, char* ws,
-                     cudaStream_t st) {
+                     int accumulate, cudaStream_t st) {
   int rc;
   if (dx) {  // dx[R,K] = dcat[R,ncat] . Wcat[ncat,K]
     GemmP p{};
@@ -386,7 +385,7 @@ int dense_bwd_common(const float* x, const float* W0, const float* W1, const flo
     rc = launch_gemm<L_XC, L_XC, EPI_SPLITK>(p, plan.S, st);
     if (rc) return rc;
     splitk_reduce_kernel<<<ew_blocks((long long)ncat * K), 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0,
-                                                                         dW1 ? dW1 : dW0);
+                                                                         dW1 ? dW1 : dW0, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
   if (db0 || db1) {
@@ -394,7 +393,7 @@ int dense_bwd_common(const float* x, const float* W0, const float* W1, const flo
     dim3 g1(ceil_div(ncat, 32), plan.S2);
     colsum_partial_kernel<<<g1, 256, 0, st>>>(dcat, R, ncat, plan.rows_per, cs);
     EXVAE_CUDA(cudaGetLastError());
-    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1);
+    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
   return EXVAE_OK;
@@ -459,7 +458,7 @@ int tc_stage_operands(const float* x, const float* W0, const float* W1, int R, i
 // dx / dW / db on the tensor cores.  dcat [R,ncat] fp32 is the pre-activation gradient.
 int dense_bwd_tc(const float* x, const float* W0, const float* W1, const float* dcat, int R, int K, int ncat, int oseg,
                  float* dx, float* dW0, float* dW1, float* db0, float* db1, const float* xs_in, const float* ws_in,
-                 const TcBwdPlan& plan, char* ws, cudaStream_t st) {
+                 const TcBwdPlan& plan, char* ws, int accumulate, cudaStream_t st) {
   float* dsplit = reinterpret_cast<float*>(ws + plan.off_dsplit);
   int rc = tc_split(dcat, (size_t)R * ncat, dsplit, (size_t)R * ncat, st);
   if (rc) return rc;
@@ -491,7 +490,7 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, const float* 
     rc = tc_gemm_launch(g, st);
     if (rc) return rc;
     splitk_reduce_kernel<<<ew_blocks((long long)ncat * K), 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0,
-                                                                         dW1 ? dW1 : dW0);
+                                                                         dW1 ? dW1 : dW0, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
   if (db0 || db1) {
@@ -499,7 +498,7 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, const float* 
     dim3 g1(ceil_div(ncat, 32), plan.S2);
     colsum_partial_kernel<<<g1, 256, 0, st>>>(dcat, R, ncat, plan.rows_per, cs);
     EXVAE_CUDA(cudaGetLastError());
-    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1);
+    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
   return EXVAE_OK;
@@ -550,7 +549,7 @@ extern "C" size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O) {
 extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin,
                                      const float* sig, const float* dout, int R, int K, int O, float* dx, float* dWh,
                                      float* dbh, float* dWg, float* dbg, const void* fwd_ws, size_t fwd_ws_bytes,
-                                     void* ws, size_t ws_bytes, exvae_stream_t stream) {
+                                     void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && Wh && Wg && h_lin && sig && dout && dWh && dWg && ws && R > 0 && K > 0 && O > 0);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
@@ -565,14 +564,14 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
     const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
     const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
     const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
-    return dense_bwd_tc(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, xs, wsp, plan, w, st);
+    return dense_bwd_tc(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, xs, wsp, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
   if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
   float* dcat = reinterpret_cast<float*>(w + plan.off_dcat);
   gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, h_lin, sig, R, O, dcat);
   EXVAE_CUDA(cudaGetLastError());
-  return dense_bwd_common(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, plan, w, st);
+  return dense_bwd_common(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, plan, w, accumulate, st);
 }
 
 extern "C" int exvae_linear_fwd(const float* x, const float* W, const float* b, int R, int K, int O, int act, float lo,
@@ -609,7 +608,8 @@ extern "C" size_t exvae_linear_bwd_workspace_bytes(int R, int K, int O) {
 
 extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out, const float* dout, int R, int K, int O,
                                 int act, float lo, float hi, float* dx, float* dW, float* db, const void* fwd_ws,
-                                size_t fwd_ws_bytes, void* ws, size_t ws_bytes, exvae_stream_t stream) {
+                                size_t fwd_ws_bytes, void* ws, size_t ws_bytes, int accumulate,
+                                exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && W && dout && dW && ws && R > 0 && K > 0 && O > 0);
   EXVAE_CHECK_ARG(act == EXVAE_ACT_NONE || out != nullptr);
   cudaStream_t st = as_stream(stream);
@@ -629,7 +629,7 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
     const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
     const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
     const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
-    return dense_bwd_tc(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, xs, wsp, plan, w, st);
+    return dense_bwd_tc(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, xs, wsp, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, O, true);
   if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
@@ -640,7 +640,7 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
     EXVAE_CUDA(cudaGetLastError());
     dpre = buf;
   }
-  return dense_bwd_common(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, plan, w, st);
+  return dense_bwd_common(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, plan, w, accumulate, st);
 }
 
 extern "C" int exvae_gemm_backend(void) { return tc_enabled() ? 1 : 0; }

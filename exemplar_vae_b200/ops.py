@@ -236,12 +236,15 @@ def unique_positions(pos, value_range: int):
 
 
 @torch.no_grad()
-def gather_rows(src, idx) -> torch.Tensor:
+def gather_rows(src, idx, out=None) -> torch.Tensor:
+    """src[idx] (rows).  ``out`` may be a contiguous [n, row] slice of a larger buffer."""
     L = lib()
     src = _f32(src)
     idx = _i64(idx).reshape(-1)
     n, row = idx.numel(), src.shape[1]
-    out = torch.empty((n, row), dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty((n, row), dtype=torch.float32, device=src.device)
+    assert out.is_contiguous() and tuple(out.shape) == (n, row) and out.dtype == torch.float32
     if n:
         L.check(L.exvae_gather_rows(_p(src), _p(idx), n, row, _p(out), _stream()), "gather_rows")
         _count(1)
@@ -266,8 +269,9 @@ def scatter_rows_(dst, idx, src) -> torch.Tensor:
 # ======================================================================================
 class _GatedDense(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, Wh, bh, Wg, bg):
+    def forward(ctx, x, Wh, bh, Wg, bg, sink):
         L = lib()
+        ctx.sink = sink
         x, Wh, Wg = _f32(x, "x"), _f32(Wh), _f32(Wg)
         bh = _f32(bh) if bh is not None else None
         bg = _f32(bg) if bg is not None else None
@@ -294,26 +298,61 @@ class _GatedDense(torch.autograd.Function):
         R, K = x.shape
         O = Wh.shape[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dWh, dWg = torch.empty_like(Wh), torch.empty_like(Wg)
-        dbh = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
-        dbg = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[1] else None
+        sink = ctx.sink
+        if sink is not None:       # fused accumulation straight into the parameters' .grad storage
+            dWh, dbh, dWg, dbg = sink
+        else:
+            dWh, dWg = torch.empty_like(Wh), torch.empty_like(Wg)
+            dbh = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
+            dbg = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[1] else None
         ws = _ws(L.exvae_gated_dense_bwd_workspace_bytes(R, K, O), x.device)
         L.check(L.exvae_gated_dense_bwd(_p(x), _p(Wh), _p(Wg), _p(h), _p(s), _p(dout), R, K, O, _p(dx), _p(dWh),
                                         _p(dbh), _p(dWg), _p(dbg), _p(fws), fws.numel() if fws is not None else 0,
-                                        _p(ws), ws.numel(), _stream()), "gated_dense_bwd")
+                                        _p(ws), ws.numel(), 1 if sink is not None else 0, _stream()),
+                "gated_dense_bwd")
         _count(6 + (1 if dx is not None else 0))
-        return dx, dWh, dbh, dWg, dbg
+        if sink is not None:
+            return dx, None, None, None, None, None
+        return dx, dWh, dbh, dWg, dbg, None
+
+
+def _grad_sink(*params):
+    """The .grad buffers of ``params`` when fused gradient accumulation is possible (every parameter
+    already owns a contiguous .grad, e.g. views of distributed.FlatGrads), else None."""
+    if not torch.is_grad_enabled() or not _FUSE_GRAD_ACCUM:
+        return None
+    out = []
+    for p in params:
+        if p is None:
+            out.append(None)
+            continue
+        g = p.grad
+        if g is None or not p.requires_grad or not g.is_contiguous() or g.dtype != torch.float32:
+            return None
+        out.append(g)
+    return tuple(out)
+
+
+_FUSE_GRAD_ACCUM = False
+
+
+def set_fused_grad_accumulation(on: bool) -> None:
+    """When on, dense layers ADD their weight/bias gradients directly into existing ``.grad`` buffers
+    inside the backward kernels (autograd then sees no gradient for those parameters)."""
+    global _FUSE_GRAD_ACCUM
+    _FUSE_GRAD_ACCUM = bool(on)
 
 
 def gated_dense(x, Wh, bh, Wg, bg) -> torch.Tensor:
     """(x Wh^T + bh) * sigmoid(x Wg^T + bg)   (utils/nn.py:44-69)."""
-    return _GatedDense.apply(x, Wh, bh, Wg, bg)
+    return _GatedDense.apply(x, Wh, bh, Wg, bg, _grad_sink(Wh, bh, Wg, bg))
 
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, b, act, lo, hi):
+    def forward(ctx, x, W, b, act, lo, hi, sink):
         L = lib()
+        ctx.sink = sink
         x, W = _f32(x, "x"), _f32(W)
         b = _f32(b) if b is not None else None
         R, K = x.shape
@@ -336,19 +375,25 @@ class _Linear(torch.autograd.Function):
         R, K = x.shape
         O = W.shape[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dW = torch.empty_like(W)
-        db = torch.empty((O,), dtype=torch.float32, device=x.device) if has_b else None
+        sink = ctx.sink
+        if sink is not None:
+            dW, db = sink
+        else:
+            dW = torch.empty_like(W)
+            db = torch.empty((O,), dtype=torch.float32, device=x.device) if has_b else None
         ws = _ws(L.exvae_linear_bwd_workspace_bytes(R, K, O), x.device)
         L.check(L.exvae_linear_bwd(_p(x), _p(W), _p(out), _p(dout), R, K, O, act, lo, hi, _p(dx), _p(dW), _p(db),
-                                   _p(fws), fws.numel() if fws is not None else 0, _p(ws), ws.numel(), _stream()),
-                "linear_bwd")
+                                   _p(fws), fws.numel() if fws is not None else 0, _p(ws), ws.numel(),
+                                   1 if sink is not None else 0, _stream()), "linear_bwd")
         _count(5 + (1 if dx is not None else 0) + (1 if act != ACT_NONE else 0))
-        return dx, dW, db, None, None, None
+        if sink is not None:
+            return dx, None, None, None, None, None, None
+        return dx, dW, db, None, None, None, None
 
 
 def linear(x, W, b=None, act: int = ACT_NONE, lo: float = 0.0, hi: float = 0.0) -> torch.Tensor:
     """act(x W^T + b)   (utils/nn.py:29-41)."""
-    return _Linear.apply(x, W, b, act, float(lo), float(hi))
+    return _Linear.apply(x, W, b, act, float(lo), float(hi), _grad_sink(W, b))
 
 
 # ======================================================================================

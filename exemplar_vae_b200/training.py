@@ -66,6 +66,7 @@ class GraphedTrainStep:
         if getattr(model, "flat_grads", None) is None:
             from .distributed import FlatGrads
             model.flat_grads = FlatGrads(model.parameters())     # stable grad pointers, one memset per step
+        ops.set_fused_grad_accumulation(True)                    # dW/db are added into the flat buffer in-kernel
         model.train()
         # eager warm-up on a side stream (allocator + optimizer state + grad buffers settle)
         s = torch.cuda.Stream()

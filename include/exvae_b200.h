@@ -134,11 +134,12 @@ EXVAE_API int exvae_gated_dense_fwd(const float* x, const float* Wh, const float
                           int K, int O, float* out, float* h_lin, float* sig, void* ws, size_t ws_bytes,
                           exvae_stream_t stream);
 EXVAE_API size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O);
-/* dx may be NULL (first layer: the input is data). */
+/* dx may be NULL (first layer: the input is data).  accumulate=1: dW/db are ADDED into the given
+ * buffers (fused gradient accumulation straight into the .grad storage) instead of overwritten. */
 EXVAE_API int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin, const float* sig,
                           const float* dout, int R, int K, int O, float* dx, float* dWh, float* dbh, float* dWg,
                           float* dbg, const void* fwd_ws, size_t fwd_ws_bytes, void* ws, size_t ws_bytes,
-                          exvae_stream_t stream);
+                          int accumulate, exvae_stream_t stream);
 /* nn.Linear / NonLinear (utils/nn.py:29-41): out = act(x W^T + b); b may be NULL. */
 EXVAE_API int exvae_linear_fwd(const float* x, const float* W, const float* b, int R, int K, int O, int act, float lo, float hi,
                      float* out, void* ws, size_t ws_bytes, exvae_stream_t stream);
@@ -146,7 +147,7 @@ EXVAE_API size_t exvae_linear_bwd_workspace_bytes(int R, int K, int O);
 /* `out` is the forward OUTPUT (post activation); dx / db may be NULL. */
 EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out, const float* dout, int R, int K, int O, int act,
                      float lo, float hi, float* dx, float* dW, float* db, const void* fwd_ws, size_t fwd_ws_bytes,
-                     void* ws, size_t ws_bytes, exvae_stream_t stream);
+                     void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream);
 /* 1 = tcgen05 3xTF32 backend active on the current device, 0 = fp32 FMA-pipe backend */
 EXVAE_API int exvae_gemm_backend(void);
 

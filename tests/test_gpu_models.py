@@ -24,8 +24,10 @@ def build(args, g=None):
     return model
 
 
-def _golden_step(g, model_name):
+def _golden_step(g, model_name, fused=False):
     import exemplar_vae_b200 as E
+    from exemplar_vae_b200 import ops
+    from exemplar_vae_b200.distributed import FlatGrads
     side = int(g["side"])
     N = len(g["ex_idx"])
     args = O.make_args(model_name=model_name, hidden_size=int(g["hidden"]), number_components=N,
@@ -52,10 +54,16 @@ def _golden_step(g, model_name):
 
     opt = E.AdamNormGrad(model.parameters(), lr=float(g["lr"]))
     model.rng_override = override()
+    model.fuse_exemplar_encoder = fused
+    if fused:        # flat gradient buffer + in-kernel accumulation + one encoder pass over batch+exemplars
+        model.flat_grads = FlatGrads(model.parameters())
+        model.flat_grads.zero_()
+    ops.set_fused_grad_accumulation(fused)
     opt.zero_grad()
     loss, RE, KL = model.calculate_loss((x, xi), beta, average=True, dataset=dataset)
     close(loss, g["loss"], rtol=1e-4); close(RE, g["RE"], rtol=1e-4); close(KL, g["KL"], rtol=1e-4)
     loss.backward()
+    ops.set_fused_grad_accumulation(False)
     for n, p in model.named_parameters():
         ref = g["g:" + n]
         scale = np.abs(ref).max() + 1e-12
@@ -77,12 +85,14 @@ def _golden_step(g, model_name):
             close(v, ref, rtol=1e-4, atol=2e-6)
 
 
-def test_vae_step_golden(golden):
-    _golden_step(golden("vae_step"), "vae")
+@pytest.mark.parametrize("fused", [False, True])
+def test_vae_step_golden(golden, fused):
+    _golden_step(golden("vae_step"), "vae", fused)
 
 
-def test_hvae_step_golden(golden):
-    _golden_step(golden("hvae_step"), "hvae_2level")
+@pytest.mark.parametrize("fused", [False, True])
+def test_hvae_step_golden(golden, fused):
+    _golden_step(golden("hvae_step"), "hvae_2level", fused)
 
 
 def test_approximate_prior_golden(golden):
