@@ -63,6 +63,19 @@ class DeviceRng:
         return out
 
 
+def to_nhwc(x, chw):
+    """[N, C*H*W] / [N,C,H,W] (the reference's NCHW) -> NHWC for the conv kernels (free when C == 1)."""
+    C, H, W = chw
+    x = x.reshape(-1, C, H, W)
+    return x.reshape(-1, H, W, 1) if C == 1 else x.permute(0, 2, 3, 1).contiguous()
+
+
+def flat_chw(h):
+    """NHWC feature map -> [N, C*H*W] flattened in the reference's (C,H,W) order."""
+    N, H, W, C = h.shape
+    return h.reshape(N, -1) if C == 1 else h.permute(0, 3, 1, 2).reshape(N, -1)
+
+
 class BaseModel(nn.Module, ABC):
     def __init__(self, args):
         super().__init__()
@@ -228,20 +241,31 @@ class BaseModel(nn.Module, ABC):
         return (torch.sigmoid(x) - lambd) / (1 - 2 * lambd)
 
     # ------------------------------------------------------------------ encoder over a bank
+    def _is_conv(self):
+        return 'conv' in self.args.model_name
+
+    def _trunk(self, x):
+        """q_z_layers over [R, P] rows; conv stacks run NHWC and return the feature map the heads expect."""
+        if self._is_conv():
+            h = self.q_z_layers(to_nhwc(x, self.args.input_size))
+            return flat_chw(h) if self.args.model_name == 'convhvae_2level' else h
+        return self.q_z_layers(x)
+
+    def _head(self, module, h):
+        out = module(h)
+        return flat_chw(out) if out.dim() == 4 else out
+
     def q_z(self, x, prior=False):
         """models/BaseModel.py:205-221 — returns (mean [R,D], logvar [R,D]).  With ``prior=True``
         under the exemplar prior the log-variance is the learned scalar broadcast (a stride-0
         view, no [R,D] tensor is written)."""
-        if 'conv' in self.args.model_name:
-            x = x.view(-1, self.args.input_size[0], self.args.input_size[1], self.args.input_size[2])
-        h = self.q_z_layers(x)
-        if self.args.model_name == 'convhvae_2level':
-            h = h.view(x.size(0), -1)
-        z_q_mean = self.q_z_mean(h)
+        R = x.shape[0]
+        h = self._trunk(x)
+        z_q_mean = self._head(self.q_z_mean, h)
         if prior is True and self.args.prior == 'exemplar_prior':
-            z_q_logvar = self.prior_log_variance.expand(x.shape[0], self.args.z1_size)
+            z_q_logvar = self.prior_log_variance.expand(R, self.args.z1_size)
         else:
-            z_q_logvar = self.q_z_logvar(h)
+            z_q_logvar = self._head(self.q_z_logvar, h)
         return z_q_mean.reshape(-1, self.args.z1_size), z_q_logvar.reshape(-1, self.args.z1_size)
 
     def q_z_with_exemplars(self, x, dataset):
@@ -255,14 +279,9 @@ class BaseModel(nn.Module, ABC):
         rows = torch.empty((B + n, P), dtype=torch.float32, device=dev)
         rows[:B].copy_(x.reshape(B, P))
         ops.gather_rows(self.resident(dataset), exemplars_indices, out=rows[B:])
-        xin = rows
-        if 'conv' in self.args.model_name:
-            xin = rows.view(-1, self.args.input_size[0], self.args.input_size[1], self.args.input_size[2])
-        h = self.q_z_layers(xin)
-        if self.args.model_name == 'convhvae_2level':
-            h = h.view(B + n, -1)
-        mean_all = self.q_z_mean(h).reshape(B + n, -1)
-        z_q_logvar = self.q_z_logvar(h[:B]).reshape(B, -1)
+        h = self._trunk(rows)
+        mean_all = self._head(self.q_z_mean, h).reshape(B + n, -1)
+        z_q_logvar = self._head(self.q_z_logvar, h[:B]).reshape(B, -1)
         ex_logvar = self.prior_log_variance.expand(n, self.args.z1_size)
         exemplar_set = (mean_all[B:], ex_logvar, exemplars_indices)
         if self.bank_group is not None:
@@ -345,17 +364,28 @@ class AbsModel(BaseModel):
         return generated_x
 
     def p_x(self, z):
-        if 'conv' in self.args.model_name:
-            z = z.reshape(-1, self.bottleneck, self.args.input_size[1] // 4, self.args.input_size[1] // 4)
-        z = self.p_x_layers(z)
-        x_mean = self.p_x_mean(z)
+        """models/AbsModel.py:31-42"""
         P = int(np.prod(self.args.input_size))
+        if self._is_conv():
+            from ._lib import ACT_HARDTANH
+            from .layers import WNConv2d
+            hw = self.args.input_size[1] // 4
+            z = to_nhwc(z, (self.bottleneck, hw, hw))
+            h = self.p_x_layers(z)
+            if self.args.input_type != 'binary' and self.args.use_logit is False and isinstance(self.p_x_mean, WNConv2d):
+                x_mean = self.p_x_mean(h, ACT_HARDTANH, 0. + 1. / 512., 1. - 1. / 512.)   # clamp fused in the epilogue
+            else:
+                x_mean = self.p_x_mean(h)
+            x_mean = flat_chw(x_mean)
+        else:
+            h = self.p_x_layers(z)
+            x_mean = self.p_x_mean(h)
+            if self.args.input_type != 'binary' and self.args.use_logit is False:
+                x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
         if self.args.input_type == 'binary':
             x_logvar = torch.zeros(1, P, device=x_mean.device)
         else:
-            if self.args.use_logit is False:
-                x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
-            x_logvar = self.decoder_logstd * x_mean.new_ones(size=x_mean.shape)
+            x_logvar = self.decoder_logstd.expand(x_mean.shape[0], P)
         return x_mean.reshape(-1, P), x_logvar.reshape(-1, P)
 
     def forward(self, x, label=0, num_categories=10, zq=None):
@@ -390,9 +420,10 @@ class BaseHModel(BaseModel):
         return self.p_z1_mean(z2), self.p_z1_logvar(z2)
 
     def q_z1(self, x, z2):
-        x = self.q_z1_layers_x(x)
-        if self.args.model_name == 'convhvae_2level':
-            x = x.view(x.size(0), -1)
+        if self._is_conv():
+            x = flat_chw(self.q_z1_layers_x(to_nhwc(x, self.args.input_size)))
+        else:
+            x = self.q_z1_layers_x(x)
         z2 = self.q_z1_layers_z2(z2)
         h = torch.cat((x, z2), 1)
         h = self.q_z1_layers_joint(h)
@@ -402,21 +433,22 @@ class BaseHModel(BaseModel):
         z1 = self.p_x_layers_z1(z1)
         z2 = self.p_x_layers_z2(z2)
         h = torch.cat((z1, z2), 1)
-        if 'convhvae_2level' in self.args.model_name:
+        conv = 'convhvae_2level' in self.args.model_name
+        if conv:
             h = self.p_x_layers_joint_pre(h)
-            h = h.view(-1, self.args.input_size[0], self.args.input_size[1], self.args.input_size[2])
+            h = to_nhwc(h, self.args.input_size)
         h_decoder = self.p_x_layers_joint(h)
         x_mean = self.p_x_mean(h_decoder)
         P = int(np.prod(self.args.input_size))
-        if 'convhvae_2level' in self.args.model_name:
-            x_mean = x_mean.view(-1, P)
+        if conv:
+            x_mean = flat_chw(x_mean)
         if self.args.input_type == 'binary':
             x_logvar = torch.zeros(1, P, device=x_mean.device)
         else:
             x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
             x_logvar = self.p_x_logvar(h_decoder)
-            if 'convhvae_2level' in self.args.model_name:
-                x_logvar = x_logvar.view(-1, P)
+            if conv:
+                x_logvar = flat_chw(x_logvar)
         return x_mean, x_logvar
 
     def forward(self, x, zq=None):

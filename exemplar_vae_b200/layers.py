@@ -82,3 +82,100 @@ class GatedDense(nn.Module):
         if self.no_attention is False:
             return ops.gated_dense(x, self.h.weight, self.h.bias, self.g.weight, self.g.bias)
         return ops.linear(x, self.h.weight, self.h.bias, ACT_RELU)
+
+
+# ----------------------------------------------------------------------------------------------
+# convolutional layers.  Activations between these modules are NHWC ([N, H, W, C]); the model
+# classes convert at the stack boundaries (free when C == 1).
+# ----------------------------------------------------------------------------------------------
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class GatedConv2d(nn.Module):
+    """utils/nn.py:72-95 — ``act(h(x)) * sigmoid(g(x))`` as one im2col + fused GEMM (h and g share the
+    patch matrix)."""
+
+    def __init__(self, input_channels, output_channels, kernel_size, stride, padding, dilation=1, activation=None,
+                 no_attention=False):
+        super().__init__()
+        if dilation != 1 or activation is not None or no_attention:
+            raise NotImplementedError("GatedConv2d: only dilation=1, activation=None, no_attention=False are used "
+                                      "by the in-scope models (the reference's no_attention branch does not run)")
+        self.no_attention = no_attention
+        self.activation = activation
+        self.sigmoid = nn.Sigmoid()
+        self.h = nn.Conv2d(input_channels, output_channels, kernel_size, stride, padding, dilation)
+        self.g = nn.Conv2d(input_channels, output_channels, kernel_size, stride, padding, dilation)
+        self._stride, self._pad = _pair(stride)[0], _pair(padding)[0]
+
+    def forward(self, x):
+        return ops.conv2d_gated(x, self.h.weight, self.h.bias, self.g.weight, self.g.bias, self._stride, self._pad)
+
+
+class Conv2d(nn.Module):
+    """utils/nn.py:100-114 — ``activation(conv(x))`` with the activation fused in the GEMM epilogue."""
+
+    def __init__(self, input_channels, output_channels, kernel_size, stride, padding, dilation=1, activation=None,
+                 bias=True):
+        super().__init__()
+        if dilation != 1:
+            raise NotImplementedError("dilation != 1")
+        self.activation = activation
+        self.conv = nn.Conv2d(input_channels, output_channels, kernel_size, stride, padding, dilation, bias=bias)
+        self._stride, self._pad = _pair(stride)[0], _pair(padding)[0]
+        self._act = _act_code(activation)
+
+    def forward(self, x):
+        act, lo, hi = self._act
+        return ops.conv2d(x, self.conv.weight, self.conv.bias, self._stride, self._pad, act, lo, hi)
+
+
+class PlainConv2d(nn.Conv2d):
+    """A bare ``nn.Conv2d`` (models/fully_conv.py:77,81) evaluated by the exvae kernels (NHWC)."""
+
+    def forward(self, x):
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0])
+
+
+class WNConv2d(nn.Module):
+    """``torch.nn.utils.weight_norm(nn.Conv2d(...))`` (models/fully_conv.py:16-17,28,...): parameters
+    ``weight_g`` [Cout,1,1,1], ``weight_v`` [Cout,Cin,kh,kw], ``bias`` — same state_dict keys;
+    w = g * v / ||v||_2 (norm over each output channel)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        ref = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        self.weight_v = nn.Parameter(ref.weight.detach().clone())
+        self.weight_g = nn.Parameter(ref.weight.detach().flatten(1).norm(dim=1).view(-1, 1, 1, 1).clone())
+        self.bias = nn.Parameter(ref.bias.detach().clone()) if bias else None
+        self._stride, self._pad = _pair(stride)[0], _pair(padding)[0]
+
+    def weight(self):
+        v = self.weight_v
+        return v * (self.weight_g / v.flatten(1).norm(dim=1).view(-1, 1, 1, 1))
+
+    def forward(self, x, act=ACT_NONE, lo=0.0, hi=0.0):
+        return ops.conv2d(x, self.weight(), self.bias, self._stride, self._pad, act, lo, hi)
+
+
+class ELU(nn.Module):
+    """torch.nn.ELU (alpha=1) on the exvae kernels."""
+
+    def forward(self, x):
+        return ops.elu(x)
+
+
+class Upsample2x(nn.Module):
+    """nn.Upsample(scale_factor=2) (nearest), NHWC."""
+
+    def forward(self, x):
+        return ops.upsample2x(x)
+
+
+class Sigmoid(nn.Module):
+    """Marker for a sigmoid that the preceding conv fuses (kept so that nn.Sequential indices — and
+    therefore state_dict keys — match the reference)."""
+
+    def forward(self, x):
+        return x

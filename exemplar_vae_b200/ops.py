@@ -326,6 +326,8 @@ def _grad_sink(*params):
         if p is None:
             out.append(None)
             continue
+        if not p.is_leaf:
+            return None
         g = p.grad
         if g is None or not p.requires_grad or not g.is_contiguous() or g.dtype != torch.float32:
             return None
@@ -728,3 +730,120 @@ def prior_lse_sharded(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total: int, gr
     Gradients: dz local (summed over shards), dmu for the local shard, dlogvar = this shard's share
     (the data-parallel gradient all-reduce completes it, like every other replicated parameter)."""
     return _PriorLSESharded.apply(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total, group)
+
+
+# ======================================================================================
+# K4: convolution = im2col -> dense GEMM (fused epilogue) -> col2im ; ELU ; 2x upsample   (NHWC)
+# ======================================================================================
+def _conv_out(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+class _Im2Col(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kh, kw, stride, pad):
+        L = lib()
+        x = _f32(x, "x")
+        N, H, W, C = x.shape
+        OH, OW = _conv_out(H, kh, stride, pad), _conv_out(W, kw, stride, pad)
+        col = torch.empty((N * OH * OW, kh * kw * C), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_im2col_nhwc(_p(x), N, H, W, C, kh, kw, stride, pad, _p(col), _stream()), "im2col")
+        _count(1)
+        ctx.cfg = (N, H, W, C, kh, kw, stride, pad)
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        L = lib()
+        N, H, W, C, kh, kw, stride, pad = ctx.cfg
+        dcol = _f32(dcol)
+        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dcol.device)
+        L.check(L.exvae_col2im_nhwc(_p(dcol), N, H, W, C, kh, kw, stride, pad, _p(dx), _stream()), "col2im")
+        _count(1)
+        return dx, None, None, None, None
+
+
+def _patches(x, kh, kw, stride, pad):
+    N, H, W, C = x.shape
+    if kh == 1 and kw == 1 and stride == 1 and pad == 0:
+        return x.reshape(N * H * W, C)
+    return _Im2Col.apply(x, kh, kw, stride, pad)
+
+
+def _w2d(w):
+    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] (channel fastest, matching the NHWC patch matrix)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def conv2d_gated(x, Wh, bh, Wg, bg, stride: int, pad: int) -> torch.Tensor:
+    """GatedConv2d (utils/nn.py:72-95, activation=None): conv_h(x) * sigmoid(conv_g(x)); x, result NHWC."""
+    N, H, W, C = x.shape
+    Cout, Cin, kh, kw = Wh.shape
+    assert Cin == C
+    col = _patches(x, kh, kw, stride, pad)
+    out = gated_dense(col, _w2d(Wh), bh, _w2d(Wg), bg)
+    return out.view(N, _conv_out(H, kh, stride, pad), _conv_out(W, kw, stride, pad), Cout)
+
+
+def conv2d(x, W, b=None, stride: int = 1, pad: int = 0, act: int = ACT_NONE, lo: float = 0.0, hi: float = 0.0):
+    """nn.Conv2d + fused activation; x, result NHWC."""
+    N, H, Wd, C = x.shape
+    Cout, Cin, kh, kw = W.shape
+    assert Cin == C
+    col = _patches(x, kh, kw, stride, pad)
+    out = linear(col, _w2d(W), b, act, lo, hi)
+    return out.view(N, _conv_out(H, kh, stride, pad), _conv_out(Wd, kw, stride, pad), Cout)
+
+
+class _Elu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L = lib()
+        x = _f32(x)
+        y = torch.empty_like(x)
+        L.check(L.exvae_elu_fwd(_p(x), x.numel(), _p(y), _stream()), "elu")
+        _count(1)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        (y,) = ctx.saved_tensors
+        dy = _f32(dy)
+        dx = torch.empty_like(y)
+        L.check(L.exvae_elu_bwd(_p(y), _p(dy), y.numel(), _p(dx), _stream()), "elu_bwd")
+        _count(1)
+        return dx
+
+
+def elu(x) -> torch.Tensor:
+    return _Elu.apply(x)
+
+
+class _Up2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L = lib()
+        x = _f32(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+        L.check(L.exvae_upsample2x_nhwc_fwd(_p(x), N, H, W, C, _p(y), _stream()), "upsample2x")
+        _count(1)
+        ctx.shape = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        N, H, W, C = ctx.shape
+        dy = _f32(dy)
+        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dy.device)
+        L.check(L.exvae_upsample2x_nhwc_bwd(_p(dy), N, H, W, C, _p(dx), _stream()), "upsample2x_bwd")
+        _count(1)
+        return dx
+
+
+def upsample2x(x) -> torch.Tensor:
+    """nn.Upsample(scale_factor=2), nearest, NHWC."""
+    return _Up2.apply(x)

@@ -12,8 +12,10 @@ def importing_model(args):
         from .vae import VAE
     elif args.model_name == 'hvae_2level':
         from .hvae_2level import VAE
-    elif args.model_name in ('convhvae_2level', 'single_conv'):
-        raise NotImplementedError(f"model_name={args.model_name!r}: the conv kernels (K4) are not built yet")
+    elif args.model_name == 'convhvae_2level':
+        from .conv_hvae_2level import VAE
+    elif args.model_name == 'single_conv':
+        from .fully_conv import VAE
     elif args.model_name == 'pixelcnn':
         raise NotImplementedError("model_name='pixelcnn' is out of scope (SURVEY.md §2)")
     else:

@@ -151,6 +151,22 @@ EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out,
 /* 1 = tcgen05 3xTF32 backend active on the current device, 0 = fp32 FMA-pipe backend */
 EXVAE_API int exvae_gemm_backend(void);
 
+/* ---------------------------------------------------------------- convolution support (K4)
+ * GatedConv2d / Conv2d (utils/nn.py:72-114) and the weight-normed conv / ELU / Upsample blocks of
+ * models/fully_conv.py:12-81 run as  im2col -> dense-layer GEMM (K3, fused gate/bias/activation)
+ * -> col2im.  Activations are NHWC; col is [N*OH*OW, kh*kw*C] with the channel fastest, where
+ * OH = (H + 2*pad - kh)/stride + 1 (same for OW).  col2im is the exact adjoint of im2col.           */
+EXVAE_API int exvae_im2col_nhwc(const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                                float* col, exvae_stream_t stream);
+EXVAE_API int exvae_col2im_nhwc(const float* dcol, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                                float* dx, exvae_stream_t stream);
+/* torch.nn.ELU (alpha = 1); the backward takes the forward OUTPUT y */
+EXVAE_API int exvae_elu_fwd(const float* x, int64_t n, float* y, exvae_stream_t stream);
+EXVAE_API int exvae_elu_bwd(const float* y, const float* dy, int64_t n, float* dx, exvae_stream_t stream);
+/* nn.Upsample(scale_factor=2) (nearest), NHWC: y [N,2H,2W,C]; backward sums each 2x2 block */
+EXVAE_API int exvae_upsample2x_nhwc_fwd(const float* x, int N, int H, int W, int C, float* y, exvae_stream_t stream);
+EXVAE_API int exvae_upsample2x_nhwc_bwd(const float* dy, int N, int H, int W, int C, float* dx, exvae_stream_t stream);
+
 /* ---------------------------------------------------------------- element-wise pieces
  * reparameterize (models/BaseModel.py:79-82): z = mu + exp(0.5 logvar) * eps (eps injected). */
 EXVAE_API int exvae_reparameterize_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, float* z,

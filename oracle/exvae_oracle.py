@@ -403,7 +403,8 @@ def init_params(args, seed=0) -> Dict[str, torch.Tensor]:
 
 
 def loss_fn(args):
-    return vae_loss if args.model_name == "vae" else hvae_loss
+    return {"vae": vae_loss, "hvae_2level": hvae_loss, "convhvae_2level": convhvae_loss,
+            "single_conv": single_conv_loss}[args.model_name]
 
 
 # ---- AdamNormGrad (utils/optimizer.py:32-80) -------------------------------------------
@@ -459,3 +460,152 @@ def synthetic_dataset(T: int, P: int = 784, seed: int = 1234) -> torch.Tensor:
     (layout of utils/load_data/base_load_data.py:55-59: x float32 [T,P], indices int64 [T,1])."""
     g = torch.Generator().manual_seed(seed)
     return torch.rand(T, P, generator=g)
+
+
+# ---- model_name == 'convhvae_2level' (models/convHVAE_2level.py:13-97, models/AbsHModel.py) ----
+_CONV_QZ = [(7, 1, 3), (3, 2, 1), (5, 1, 2), (3, 2, 1), (3, 1, 1)]      # (kernel, stride, padding) of q_z_layers
+_CONV_QZ1 = [(3, 1, 1), (3, 2, 1), (3, 1, 1), (3, 2, 1), (3, 1, 1)]     # q_z1_layers_x
+
+
+def _gated_stack(p, name, x, spec):
+    for i, (k, s, pd) in enumerate(spec):
+        x = t_gated_conv(p, f"{name}.{i}", x, s, pd)
+    return x
+
+
+def convhvae_q_z(p, args, x, prior=False):
+    """models/BaseModel.py:205-221 for convhvae_2level: 5 gated convs -> flatten (C,H,W) -> linear heads."""
+    C, H, W = args.input_size
+    h = _gated_stack(p, "q_z_layers", x.view(-1, C, H, W), _CONV_QZ).reshape(x.shape[0], -1)
+    mean = _lin(p, "q_z_mean.linear", h)
+    if prior and args.prior == "exemplar_prior":
+        logvar = p["prior_log_variance"] * torch.ones((x.shape[0], args.z1_size))
+    else:
+        logvar = t_hardtanh_linear(p, "q_z_logvar", h)
+    return mean, logvar
+
+
+def convhvae_loss(p, args, x, x_indices, eps2, eps1, exemplars, exemplar_indices, beta=1.0, average=True,
+                  masked=True, exemplars_embedding=None):
+    """models/AbsHModel.py:13-29,45-106 for convhvae_2level, binary input, RNG injected."""
+    C, H, W = args.input_size
+    z2_mean, z2_logvar = convhvae_q_z(p, args, x)
+    z2 = z2_mean + torch.exp(0.5 * z2_logvar) * eps2
+    hx = _gated_stack(p, "q_z1_layers_x", x.view(-1, C, H, W), _CONV_QZ1).reshape(x.shape[0], -1)
+    hz = t_gated_dense(p, "q_z1_layers_z2.0", z2)
+    hj = t_gated_dense(p, "q_z1_layers_joint.0", torch.cat((hx, hz), 1))
+    z1_mean = _lin(p, "q_z1_mean.linear", hj)
+    z1_logvar = t_hardtanh_linear(p, "q_z1_logvar", hj)
+    z1 = z1_mean + torch.exp(0.5 * z1_logvar) * eps1
+    hp = t_gated_dense(p, "p_z1_layers_z2.1", t_gated_dense(p, "p_z1_layers_z2.0", z2))
+    z1_p_mean = _lin(p, "p_z1_mean.linear", hp)
+    z1_p_logvar = t_hardtanh_linear(p, "p_z1_logvar", hp)
+    d = torch.cat((t_gated_dense(p, "p_x_layers_z1.0", z1), t_gated_dense(p, "p_x_layers_z2.0", z2)), 1)
+    d = t_gated_dense(p, "p_x_layers_joint_pre.0", d).view(-1, C, H, W)
+    d = _gated_stack(p, "p_x_layers_joint", d, [(3, 1, 1)] * 4)
+    x_mean = torch.sigmoid(torch.nn.functional.conv2d(d, p["p_x_mean.conv.weight"], p["p_x_mean.conv.bias"]))
+    RE = t_log_bernoulli(x, x_mean.reshape(x.shape[0], -1))
+    if exemplars_embedding is None:
+        ex_mean, ex_logvar = convhvae_q_z(p, args, exemplars, prior=True)
+        ex_idx = exemplar_indices
+    else:
+        ex_mean, ex_logvar, ex_idx = exemplars_embedding
+    KL = -(t_log_normal_diag(z1, z1_p_mean, z1_p_logvar) + t_log_p_z_exemplar(z2, x_indices, ex_mean, ex_logvar[0], ex_idx, masked)
+           - t_log_normal_diag(z1, z1_mean, z1_logvar) - t_log_normal_diag(z2, z2_mean, z2_logvar))
+    loss = -RE + beta * KL
+    if average:
+        return loss.mean(), RE.mean(), KL.mean()
+    return loss, RE, KL
+
+
+# ---- model_name == 'single_conv' (models/fully_conv.py:12-81, models/AbsModel.py) -------------
+def _wn_conv(p, name, x, stride=1):
+    """torch.nn.utils.weight_norm(nn.Conv2d(k=3, padding=1)): w = g * v / ||v|| per output channel."""
+    v, g = p[name + ".weight_v"], p[name + ".weight_g"]
+    w = v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1, 1))
+    return torch.nn.functional.conv2d(x, w, p.get(name + ".bias"), stride=stride, padding=1)
+
+
+def _res_blocks(p, name, x, first):
+    elu = torch.nn.functional.elu
+    for i in range(first, first + 6):                      # block: x + conv1(ELU(x))   fully_conv.py:13-23
+        x = x + _wn_conv(p, f"{name}.{i}.conv1", elu(x))
+    return x
+
+
+def single_conv_q_z(p, args, x, prior=False):
+    elu = torch.nn.functional.elu
+    C, H, W = args.input_size
+    h = elu(_wn_conv(p, "q_z_layers.0", x.view(-1, C, H, W), stride=2))
+    h = _res_blocks(p, "q_z_layers", h, 2)
+    h = elu(_wn_conv(p, "q_z_layers.8", h, stride=2))
+    h = _res_blocks(p, "q_z_layers", h, 10)
+    mean = _wn_conv(p, "q_z_mean", h).reshape(-1, args.z1_size)
+    if prior and args.prior == "exemplar_prior":
+        logvar = p["prior_log_variance"] * torch.ones((x.shape[0], args.z1_size))
+    else:
+        logvar = _wn_conv(p, "q_z_logvar", h).reshape(-1, args.z1_size)
+    return mean, logvar
+
+
+def single_conv_loss(p, args, x, x_indices, eps, exemplars, exemplar_indices, beta=1.0, average=True, masked=True,
+                     exemplars_embedding=None):
+    """models/AbsModel.py:13-49 with the fully-conv architecture; binary or continuous (logistic-256) input."""
+    elu = torch.nn.functional.elu
+    up = lambda t: torch.nn.functional.interpolate(t, scale_factor=2)
+    C, H, W = args.input_size
+    mean, logvar = single_conv_q_z(p, args, x)
+    z = mean + torch.exp(0.5 * logvar) * eps
+    h = z.reshape(-1, args.bottleneck, H // 4, W // 4)
+    h = elu(_wn_conv(p, "p_x_layers.1", up(h)))
+    h = _res_blocks(p, "p_x_layers", h, 3)
+    h = elu(_wn_conv(p, "p_x_layers.10", up(h)))
+    h = _res_blocks(p, "p_x_layers", h, 12)
+    P = C * H * W
+    if args.input_type == "binary":
+        x_mean = torch.sigmoid(torch.nn.functional.conv2d(h, p["p_x_mean.0.weight"], p["p_x_mean.0.bias"], padding=1))
+        RE = t_log_bernoulli(x, x_mean.reshape(-1, P))
+    else:
+        x_mean = torch.clamp(_wn_conv(p, "p_x_mean", h), min=1. / 512., max=1. - 1. / 512.).reshape(-1, P)
+        x_logvar = p["decoder_logstd"] * torch.ones_like(x_mean)
+        RE = t_log_logistic_256(x, x_mean, x_logvar)
+    if exemplars_embedding is None:
+        ex_mean, ex_logvar = single_conv_q_z(p, args, exemplars, prior=True)
+        ex_idx = exemplar_indices
+    else:
+        ex_mean, ex_logvar, ex_idx = exemplars_embedding
+    log_p = t_log_p_z_exemplar(z, x_indices, ex_mean, ex_logvar[0], ex_idx, masked)
+    KL = -(log_p - t_log_normal_diag(z, mean, logvar))
+    loss = -RE + beta * KL
+    if average:
+        return loss.mean(), RE.mean(), KL.mean()
+    return loss, RE, KL
+
+
+# ---- deterministic synthetic parameters (large conv models: fixtures store seeds, not tensors) ----
+def synth_params(shapes: Dict[str, tuple], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Reproducible parameter values keyed by state_dict name: N(0, 1/fan_in) weights, small biases,
+    positive weight-norm gains.  BatchNorm tensors of the never-applied ``block.normalization``
+    (models/fully_conv.py:16) and integer buffers are left out (callers keep their own)."""
+    import zlib
+    out = {}
+    for key in sorted(shapes):
+        shape = tuple(shapes[key])
+        if "normalization" in key or "num_batches_tracked" in key:
+            continue
+        # fully_conv blocks expose conv1 twice in the state_dict (``conv1.*`` and ``f.1.*``, one tensor)
+        canon = key.replace(".f.1.", ".conv1.")
+        g = torch.Generator().manual_seed((zlib.crc32(canon.encode()) + 7919 * seed) & 0x7FFFFFFF)
+        if key == "prior_log_variance":
+            v = torch.full(shape, -1.3)
+        elif key == "decoder_logstd":
+            v = torch.full(shape, -0.4)
+        elif key.endswith("weight_g"):
+            v = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            v = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+        else:
+            v = 0.1 * torch.randn(shape, generator=g)
+        out[key] = v
+    return out

@@ -172,35 +172,50 @@ def _step(model, args, x, x_idx, eps_list, ex_idx, dataset, beta, cache=None):
     return loss, RE, KL, grads, new, (l2, re2, kl2)
 
 
-def golden_model_step(model_name, hidden, seed, side=28):
-    """a5, a8-a11, a14, a16-a19 (+ AdamNormGrad): one training step of the exact exemplar prior."""
-    T, N, B = 128, 64, 12
-    P = side * side
+def golden_model_step(model_name, hidden, seed, side=28, T=128, N=64, B=12, chans=1, D=40, **extra):
+    """a5, a8-a19 (+ AdamNormGrad): one training step of the exact exemplar prior."""
+    P = chans * side * side
     args = ref_args(model_name=model_name, hidden_size=hidden, number_components=N, training_set_size=T, batch_size=B,
-                    input_size=[1, side, side])
+                    input_size=[chans, side, side], z1_size=D, z2_size=D, **extra)
     model = build_ref_model(args, seed)
     with torch.no_grad():
         model.prior_log_variance.fill_(-1.3)
+    compact = extra.pop("_compact", False) if False else model_name in ("convhvae_2level", "single_conv")
+    if compact:     # big models: parameters are regenerated from seeds by the tests (oracle.synth_params)
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+        from oracle.exvae_oracle import synth_params
+        sp = synth_params({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed)
+        model.load_state_dict(sp, strict=False)
     g = torch.Generator().manual_seed(seed + 1)
     data = torch.rand(T, P, generator=g)
     dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
     bidx = torch.randperm(T, generator=g)[:B]
-    x = torch.bernoulli(data[bidx], generator=g)
+    x = torch.bernoulli(data[bidx], generator=g) if args.input_type == "binary" else data[bidx].clone()
     x_idx = bidx.view(-1, 1)
     ex_idx = torch.randint(0, T, (N,), generator=g)
-    ex_idx[:4] = bidx[:4]                                  # guarantee leave-one-out hits
-    n_eps = 1 if model_name == "vae" else 2
-    eps_list = [torch.randn(B, 40, generator=g) for _ in range(n_eps)]
+    ex_idx[:3] = bidx[:3]                                  # guarantee leave-one-out hits
+    n_eps = 1 if model_name in ("vae", "single_conv") else 2
+    eps_list = [torch.randn(B, D, generator=g) for _ in range(n_eps)]
     beta = 0.37
     before = sd_np(model)
+    import warnings
+    warnings.simplefilter("ignore")
     loss, RE, KL, grads, new, per = _step(model, args, x, x_idx, [e.clone() for e in eps_list], ex_idx, dataset, beta)
-    out = dict(before)
-    out.update(grads); out.update(new)
+    if compact:   # keep norms + the first 48 entries of every gradient / updated tensor
+        head = lambda a: np.asarray(a).reshape(-1)[:48].copy()
+        out = {"shape:" + k[2:]: np.asarray(v.shape, dtype=np.int64) for k, v in before.items()}
+        out.update({"gh:" + k[2:]: head(v) for k, v in grads.items()})
+        out.update({"gn:" + k[2:]: np.float64(np.linalg.norm(np.asarray(v, dtype=np.float64))) for k, v in grads.items()})
+        out.update({"nh:" + k[2:]: head(v) for k, v in new.items() if v.dtype == np.float32})
+        out["seed"] = np.int64(seed)
+    else:
+        out = dict(before)
+        out.update(grads); out.update(new)
     out.update({"x": x.numpy(), "x_idx": x_idx.numpy(), "ex_idx": ex_idx.numpy(), "exemplars": data[ex_idx].numpy(),
                 "beta": np.float32(beta), "lr": np.float32(args.lr), "hidden": np.int64(hidden),
                 "loss": loss.detach().numpy(), "RE": RE.detach().numpy(), "KL": KL.detach().numpy(),
                 "loss_b": per[0].numpy(), "RE_b": per[1].numpy(), "KL_b": per[2].numpy(),
-                "T": np.int64(T), "side": np.int64(side)})
+                "T": np.int64(T), "side": np.int64(side), "chans": np.int64(chans), "D": np.int64(D)})
     for i, e in enumerate(eps_list):
         out[f"eps{i}"] = e.numpy()
     return out
@@ -254,6 +269,11 @@ def main():
     np.savez_compressed(os.path.join(OUT, "vae_step.npz"), **golden_model_step("vae", 48, 3))
     np.savez_compressed(os.path.join(OUT, "hvae_step.npz"), **golden_model_step("hvae_2level", 24, 4, side=14))
     np.savez_compressed(os.path.join(OUT, "approx.npz"), **golden_approx())
+    np.savez_compressed(os.path.join(OUT, "convhvae_step.npz"),
+                        **golden_model_step("convhvae_2level", 300, 6, side=28, T=24, N=6, B=4))
+    np.savez_compressed(os.path.join(OUT, "single_conv_step.npz"),
+                        **golden_model_step("single_conv", 300, 8, side=8, T=24, N=6, B=4, chans=3, D=8,
+                                            input_type="continuous", bottleneck=2))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -364,3 +364,51 @@ def test_cpu_tensor_is_rejected(ops):
     from exemplar_vae_b200 import ExvaeError
     with pytest.raises(ExvaeError):
         ops.pairwise_distance(torch.randn(3, 4), torch.randn(5, 4))
+
+
+# ------------------------------------------------------------------ K4 (conv = im2col + GEMM + col2im)
+@pytest.mark.parametrize("N,C,H,Cout,k,s,p", [(3, 1, 28, 32, 7, 1, 3), (2, 32, 14, 64, 5, 1, 2), (2, 32, 28, 32, 3, 2, 1),
+                                              (2, 64, 7, 6, 3, 1, 1), (2, 3, 8, 48, 3, 2, 1), (2, 64, 28, 1, 1, 1, 0)])
+def test_gated_conv2d_fwd_bwd(ops, N, C, H, Cout, k, s, p):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(N + C + H + Cout + k)
+    x = torch.randn(N, C, H, H, generator=g)
+    Wh = torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5
+    Wg = torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5
+    bh, bg = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    ts = [t.double().requires_grad_(True) for t in (x, Wh, bh, Wg, bg)]
+    ref = F.conv2d(ts[0], ts[1], ts[2], stride=s, padding=p) * torch.sigmoid(F.conv2d(ts[0], ts[3], ts[4], stride=s, padding=p))
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout.double())
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)          # NHWC
+    cs = [t.cuda().requires_grad_(True) for t in (Wh, bh, Wg, bg)]
+    out = ops.conv2d_gated(xc, cs[0], cs[1], cs[2], cs[3], s, p)
+    close(out.permute(0, 3, 1, 2), ref, rtol=2e-5, atol=3e-5)
+    out.backward(dout.permute(0, 2, 3, 1).contiguous().cuda())
+    close(xc.grad.permute(0, 3, 1, 2), ts[0].grad, rtol=1e-4, atol=1e-4)
+    for c, t in zip(cs, ts[1:]):
+        close(c.grad, t.grad, rtol=1e-4, atol=2e-4)
+    # plain conv + fused sigmoid
+    out2 = ops.conv2d(xc.detach(), cs[0].detach(), cs[1].detach(), s, p, 1)
+    close(out2.permute(0, 3, 1, 2), torch.sigmoid(F.conv2d(ts[0], ts[1], ts[2], stride=s, padding=p)), rtol=2e-5, atol=3e-5)
+
+
+def test_elu_upsample(ops):
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 5, 6, 4, generator=g)
+    xd = x.clone().requires_grad_(True)
+    xc = x.cuda().requires_grad_(True)
+    w = torch.randn(3, 5, 6, 4, generator=g)
+    (F.elu(xd) * w).sum().backward()
+    y = ops.elu(xc); (y * w.cuda()).sum().backward()
+    close(y, F.elu(x), rtol=1e-6, atol=1e-7); close(xc.grad, xd.grad, rtol=1e-6, atol=1e-7)
+    xd2 = x.permute(0, 3, 1, 2).clone().requires_grad_(True)                       # NCHW for torch
+    up = F.interpolate(xd2, scale_factor=2)
+    w2 = torch.randn(up.shape, generator=g)
+    (up * w2).sum().backward()
+    xc2 = x.cuda().requires_grad_(True)
+    u = ops.upsample2x(xc2)
+    close(u.permute(0, 3, 1, 2), up, rtol=0)
+    (u * w2.permute(0, 2, 3, 1).contiguous().cuda()).sum().backward()
+    close(xc2.grad.permute(0, 3, 1, 2), xd2.grad, rtol=1e-6, atol=1e-6)

@@ -208,3 +208,52 @@ def test_checkpoint_roundtrip(tmp_path):
     assert ck["epoch"] == 1
     for a, b in zip(m.parameters(), m2.parameters()):
         assert torch.equal(a, b)
+
+
+def _compact_step(g, model_name):
+    """Conv models: parameters regenerated from seeds (oracle.synth_params), checked against gradient
+    summaries and losses recorded from the reference."""
+    import exemplar_vae_b200 as E
+    side, chans, D = int(g["side"]), int(g["chans"]), int(g["D"])
+    kw = dict(input_type="continuous", bottleneck=2) if model_name == "single_conv" else {}
+    N = len(g["ex_idx"]); T = int(g["T"])
+    args = O.make_args(model_name=model_name, hidden_size=int(g["hidden"]), number_components=N, training_set_size=T,
+                       input_size=[chans, side, side], z1_size=D, z2_size=D, device="cuda", **kw)
+    model = build(args)
+    shapes = {k[6:]: tuple(int(v) for v in g[k]) for k in g if k.startswith("shape:")}
+    missing = model.load_state_dict(O.synth_params(shapes, int(g["seed"])), strict=False)
+    assert all("normalization" in k for k in missing.missing_keys), missing
+    model.train()
+    P = chans * side * side
+    data = torch.zeros(T, P)
+    data[torch.tensor(g["ex_idx"])] = torch.tensor(g["exemplars"])
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    n_eps = 1 if model_name == "single_conv" else 2
+    x = torch.tensor(g["x"]).cuda(); xi = torch.tensor(g["x_idx"]).cuda()
+    beta = float(g["beta"])
+    for fused in (False, True):
+        model.fuse_exemplar_encoder = fused
+        model.rng_override = {"eps": [torch.tensor(g[f"eps{i}"]).cuda() for i in range(n_eps)],
+                              "exemplar_indices": torch.tensor(g["ex_idx"]).cuda()}
+        model.zero_grad(set_to_none=True)
+        loss, RE, KL = model.calculate_loss((x, xi), beta, average=True, dataset=dataset)
+        close(loss, g["loss"], rtol=1e-4); close(RE, g["RE"], rtol=1e-4); close(KL, g["KL"], rtol=1e-4)
+        loss.backward()
+        seen = 0
+        for n_, p in model.named_parameters():
+            if ("gn:" + n_) not in g:
+                continue
+            seen += 1
+            gr = p.grad.detach().cpu().numpy()
+            close(np.linalg.norm(gr.astype(np.float64)), g["gn:" + n_], rtol=5e-3)
+            ref = g["gh:" + n_]
+            close(gr.reshape(-1)[:48], ref, rtol=1e-2, atol=5e-3 * (np.abs(ref).max() + 1e-8))
+        assert seen > 50
+
+
+def test_convhvae_step_golden(golden):
+    _compact_step(golden("convhvae_step"), "convhvae_2level")
+
+
+def test_single_conv_step_golden(golden):
+    _compact_step(golden("single_conv_step"), "single_conv")

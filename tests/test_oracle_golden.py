@@ -158,3 +158,34 @@ def test_lse_partial_merge_is_associative():
     m = np.stack([p.max(1) for p in parts]); s = np.stack([np.exp(p - p.max(1, keepdims=True)).sum(1) for p in parts])
     M, S = O.merge_lse_partials_np(m, s)
     np.testing.assert_allclose(M + np.log(S), full, rtol=1e-12)
+
+
+def _compact_check(g, model_name):
+    side, chans, D = int(g["side"]), int(g["chans"]), int(g["D"])
+    kw = dict(input_type="continuous", bottleneck=2) if model_name == "single_conv" else {}
+    args = O.make_args(model_name=model_name, hidden_size=int(g["hidden"]), number_components=len(g["ex_idx"]),
+                       training_set_size=int(g["T"]), input_size=[chans, side, side], z1_size=D, z2_size=D, **kw)
+    shapes = {k[6:]: tuple(int(v) for v in g[k]) for k in g if k.startswith("shape:")}
+    p = {k: v.requires_grad_(True) for k, v in O.synth_params(shapes, int(g["seed"])).items()}
+    x = torch.tensor(g["x"]); xi = torch.tensor(g["x_idx"]); ex = torch.tensor(g["exemplars"])
+    ei = torch.tensor(g["ex_idx"]); beta = float(g["beta"])
+    eps = [torch.tensor(g[f"eps{i}"]) for i in range(1 if model_name == "single_conv" else 2)]
+    loss, RE, KL = O.loss_fn(args)(p, args, x, xi, *eps, ex, ei, beta=beta, average=True)
+    _close(loss.item(), g["loss"], rtol=2e-5)
+    _close(RE.item(), g["RE"], rtol=2e-5)
+    _close(KL.item(), g["KL"], rtol=2e-5)
+    loss.backward()
+    for k in g:
+        if k.startswith("gn:"):
+            name = k[3:]
+            gr = p[name].grad.numpy()
+            _close(np.linalg.norm(gr.astype(np.float64)), g[k], rtol=2e-3)
+            _close(gr.reshape(-1)[:48], g["gh:" + name], rtol=5e-3, atol=2e-3 * (np.abs(g["gh:" + name]).max() + 1e-8))
+
+
+def test_convhvae_training_step(golden):
+    _compact_check(golden("convhvae_step"), "convhvae_2level")
+
+
+def test_single_conv_training_step(golden):
+    _compact_check(golden("single_conv_step"), "single_conv")
