@@ -665,6 +665,11 @@ extern "C" size_t exvae_prior_lse_workspace_bytes(int B, int C, int D) {
   return prior_ws_layout(B, C, D, true, nullptr).bytes;
 }
 
+extern "C" size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D) {
+  if (B <= 0 || C <= 0 || D <= 0) return 0;
+  return prior_ws_layout(B, C, D, false, nullptr).bytes;
+}
+
 extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
                                    const int64_t* mu_idx, int B, int C, int D, float* stats, void* ws, size_t ws_bytes,
                                    exvae_stream_t stream) {

@@ -91,7 +91,9 @@ class _PriorLSE(torch.autograd.Function):
         if mu_idx is not None:
             mu_idx = mu_idx.reshape(-1)
             assert mu_idx.numel() == C
-        ws = _ws(L.exvae_prior_lse_workspace_bytes(B, C, D), z.device)
+        need_bwd = any(ctx.needs_input_grad)
+        ws = _ws(L.exvae_prior_lse_workspace_bytes(B, C, D) if need_bwd else
+                 L.exvae_prior_lse_fwd_workspace_bytes(B, C, D), z.device)
         stats = torch.empty((B, 4), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(stats), _p(ws),
                                       ws.numel(), _stream()), "prior_lse_fwd")

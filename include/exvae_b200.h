@@ -69,7 +69,8 @@ EXVAE_API int exvae_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * bwd: given dL/dlog_p returns dz [B,D] (partial over this shard), dmu [C,D] (complete for
  * this shard) and dlogvar [D] (partial over this shard).
  */
-EXVAE_API size_t exvae_prior_lse_workspace_bytes(int B, int C, int D);
+EXVAE_API size_t exvae_prior_lse_workspace_bytes(int B, int C, int D);     /* forward + backward */
+EXVAE_API size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D); /* forward only (evaluation) */
 EXVAE_API int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
                         const int64_t* mu_idx, int B, int C, int D, float* stats /*[B,4]*/, void* ws,
                         size_t ws_bytes, exvae_stream_t stream);

@@ -257,3 +257,49 @@ def test_convhvae_step_golden(golden):
 
 def test_single_conv_step_golden(golden):
     _compact_step(golden("single_conv_step"), "single_conv")
+
+
+def test_evaluate_loss_and_iwae_vs_oracle():
+    """validation ELBO over the full-train bank and IWAE likelihood, against the oracle."""
+    import exemplar_vae_b200 as E
+    from exemplar_vae_b200.evaluation import calculate_likelihood, evaluate_loss, load_all_pseudo_input
+    T, V = 600, 40
+    args = O.make_args(model_name="vae", hidden_size=64, number_components=100, training_set_size=T, device="cuda")
+    p = O.init_params(args, seed=2)
+    model = build(args)
+    model.load_state_dict({k: v.detach().clone() for k, v in p.items()})
+    data = O.synthetic_dataset(T)
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    g = torch.Generator().manual_seed(3)
+    val = torch.bernoulli(torch.rand(V, 784, generator=g), generator=g)
+    vset = torch.utils.data.TensorDataset(val, torch.zeros(V))
+    loader = torch.utils.data.DataLoader(vset, batch_size=16)
+    bank = load_all_pseudo_input(args, model, dataset)
+    with torch.no_grad():
+        ref_mean, ref_lv = O.vae_q_z(p, args, data, prior=True)
+    close(bank[0], ref_mean, rtol=1e-4, atol=1e-5)
+    # evaluate_loss with injected eps
+    eps = torch.randn(V, 40, generator=g)
+    model.rng_override = {"eps": [eps[i:i + 16].cuda() for i in range(0, V, 16)]}
+    elbo, re, kl = evaluate_loss(args, model, loader, dataset=dataset, exemplars_embedding=bank)
+    with torch.no_grad():
+        l, r, k = O.vae_loss(p, args, val, None, eps, None, None, average=False, masked=False,
+                             exemplars_embedding=(ref_mean, ref_lv, torch.arange(T)))
+    close(elbo, l.mean(), rtol=1e-4); close(re, -r.mean(), rtol=1e-4); close(kl, k.mean(), rtol=1e-4)
+    # IWAE with S=64 samples on 3 images
+    S = 64
+    eps_s = [torch.randn(S, 40, generator=g) for _ in range(3)]
+    model.rng_override = {"eps": [e.cuda() for e in eps_s]}
+    small = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(val[:3], torch.zeros(3)), batch_size=1)
+    nll = calculate_likelihood(args, model, small, S=S, exemplars_embedding=bank)
+    ref = []
+    with torch.no_grad():
+        for i in range(3):
+            l, _, _ = O.vae_loss(p, args, val[i:i + 1].expand(S, -1), None, eps_s[i], None, None, average=False,
+                                 masked=False, exemplars_embedding=(ref_mean, ref_lv, torch.arange(T)))
+            ref.append(torch.logsumexp(-l.double(), 0) - np.log(S))
+    close(nll, -torch.stack(ref).mean(), rtol=1e-4)
+    from exemplar_vae_b200.knn_on_latent import find_nearest_neighbors
+    nn = find_nearest_neighbors(bank[0][:7], bank[0])
+    assert np.array_equal(nn.cpu().numpy(), O.find_nearest_neighbors_np(ref_mean[:7].numpy(), ref_mean.numpy(), 20)) \
+        or np.array_equal(nn.cpu().numpy()[:, 0], np.arange(7))
