@@ -18,7 +18,10 @@
 // D = 40 is not an MMA-friendly K and the 1e-4 parity bar excludes tf32/bf16 operands
 // (SURVEY.md §7), so the contraction runs on the fp32 FMA pipe with an 8x4 register tile per
 // thread; the tensor-core variant only pays for D >= 64 and is a later-round item.
+#include <algorithm>
+
 #include "common.cuh"
+#include "prior_lse_tc.cuh"
 
 namespace exvae {
 namespace {
@@ -30,8 +33,15 @@ constexpr int PR_TM = 8;
 constexpr int PR_TN = 4;
 constexpr int64_t kPadIdx = INT64_MIN;
 
+constexpr int PR_MAXM = 8;       // masked columns per row kept in the fast list of the tensor-core path
+
 struct PriorWs {
   int LD, kch, Bpad, Cpad, nsplit, ntile;
+  int KP;                // tensor-core path: augmented, 8-padded K (0 = path not applicable)
+  float* zp;             // [2, Bpad, KP] hi/lo planes of (zs*log2e | 1)
+  float* mp;             // [2, Cpad, KP] hi/lo planes of (ms | nb2)
+  int* mcnt;             // [Bpad] number of masked columns per row
+  int* mlist;            // [Bpad, PR_MAXM] their positions
   float* zs;
   float* hz;
   float* ms;
@@ -73,7 +83,17 @@ inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
   w.nb2 = (float*)take(sizeof(float) * w.Cpad);
   w.cidx = (int64_t*)take(sizeof(int64_t) * w.Cpad);
   w.isig = (float*)take(sizeof(float) * w.LD);
-  w.part = (float*)take(sizeof(float) * 4 * (size_t)w.Bpad * w.nsplit);
+  w.part = (float*)take(sizeof(float) * 4 * (size_t)w.Bpad * (size_t)std::max(w.nsplit, 2 * sm_count()));
+  w.KP = (D + 1 <= 64) ? ceil_div(D + 1, 8) * 8 : 0;
+  if (w.KP) {
+    w.zp = (float*)take(sizeof(float) * 2 * (size_t)w.Bpad * w.KP);
+    w.mp = (float*)take(sizeof(float) * 2 * (size_t)w.Cpad * w.KP);
+    w.mcnt = (int*)take(sizeof(int) * w.Bpad);
+    w.mlist = (int*)take(sizeof(int) * (size_t)w.Bpad * PR_MAXM);
+  } else {
+    w.zp = w.mp = nullptr;
+    w.mcnt = w.mlist = nullptr;
+  }
   if (need_bwd) {
     w.dzs_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.Bpad * w.LD);
     w.rowsum_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.Bpad);
@@ -96,7 +116,8 @@ __global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restric
                                                           int LD, int Bpad, int Cpad, float* __restrict__ zs,
                                                           float* __restrict__ hz, float* __restrict__ ms,
                                                           float* __restrict__ nb2, int64_t* __restrict__ cidx,
-                                                          float* __restrict__ isig) {
+                                                          float* __restrict__ isig, int KP, float* __restrict__ zp,
+                                                          float* __restrict__ mp, int* __restrict__ mcnt) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x < LD) {
@@ -109,6 +130,18 @@ __global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restric
   const bool valid = is_bank ? (r < C) : (r < B);
   const float* src = is_bank ? mu + (size_t)r * D : z + (size_t)r * D;
   float* dst = is_bank ? ms + (size_t)r * LD : zs + (size_t)r * LD;
+  // tensor-core operands: hi = tf32(x), lo = tf32(x - hi) planes of the augmented rows
+  //   z' = (zs * log2e | 1 | 0..)      m' = (ms | nb2 | 0..)      so that  z'.m' = logit2
+  const size_t plane = (size_t)(is_bank ? Cpad : Bpad) * KP;
+  float* sp = KP ? (is_bank ? mp : zp) + (size_t)r * KP : nullptr;
+  auto put_split = [&](int d, float x) {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+    const float hf = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - hf));
+    sp[d] = hf;
+    sp[plane + d] = __uint_as_float(lb);
+  };
   float ss = 0.f;
   for (int d = lane; d < LD; d += 32) {
     float v = 0.f;
@@ -116,15 +149,48 @@ __global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restric
     dst[d] = v;
     ss = fmaf(v, v, ss);
   }
+  if (KP)
+    for (int d = lane; d < KP; d += 32) {
+      if (d == D) continue;            // augmented column, written below once the norm is known
+      float v = 0.f;
+      if (valid && d < D) v = src[d] / expf(0.5f * logvar[d]);
+      put_split(d, is_bank ? v : v * kLog2e);
+    }
   ss = warp_sum(ss);
   if (lane == 0) {
     if (is_bank) {
       nb2[r] = valid ? -0.5f * ss * kLog2e : -INFINITY;
       cidx[r] = valid ? (mu_idx ? mu_idx[r] : (int64_t)-1) : kPadIdx;
+      if (KP) put_split(D, valid ? -0.5f * ss * kLog2e : -1e30f);   // finite "minus infinity" for padded columns
     } else {
       hz[r] = 0.5f * ss;
+      if (KP) {
+        put_split(D, valid ? 1.0f : 0.f);
+        mcnt[r] = 0;
+      }
     }
   }
+}
+
+// masked-pair list for the tensor-core path: mcnt[b] = #{n : mu_idx[n] == z_idx[b]}, first PR_MAXM positions
+__global__ void __launch_bounds__(256) prior_mask_list_kernel(const int64_t* __restrict__ z_idx,
+                                                              const int64_t* __restrict__ mu_idx, int B, int C,
+                                                              int* __restrict__ mcnt, int* __restrict__ mlist) {
+  // grid = (column chunks of 256, row chunks of 128): every thread compares its column with 128 rows
+  __shared__ long long zs_idx[128];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * 128;
+  const int nb = min(128, B - b0);
+  if (threadIdx.x < nb) zs_idx[threadIdx.x] = z_idx[b0 + threadIdx.x];
+  __syncthreads();
+  if (n >= C) return;
+  const long long mine = mu_idx[n];
+#pragma unroll 8
+  for (int i = 0; i < nb; ++i)
+    if (zs_idx[i] == mine) {
+      const int slot = atomicAdd(&mcnt[b0 + i], 1);
+      if (slot < PR_MAXM) mlist[(size_t)(b0 + i) * PR_MAXM + slot] = n;
+    }
 }
 
 // ------------------------------------------------------------------------------- forward
@@ -650,7 +716,8 @@ int stage(const PriorWs& w, const float* z, const float* mu, const float* logvar
           int D, cudaStream_t st) {
   const int rows = w.Cpad + w.Bpad;
   prior_stage_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, mu, logvar, mu_idx, B, C, D, w.LD, w.Bpad, w.Cpad, w.zs,
-                                                        w.hz, w.ms, w.nb2, w.cidx, w.isig);
+                                                        w.hz, w.ms, w.nb2, w.cidx, w.isig, w.KP, w.zp, w.mp,
+                                                        w.mcnt);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
@@ -684,6 +751,22 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
   int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, st);
   if (rc) return rc;
   const bool mask = z_idx && mu_idx;
+  if (w.KP && prior_tc_enabled()) {
+    if (mask) {
+      prior_mask_list_kernel<<<dim3(ceil_div(C, 256), ceil_div(B, 128)), 256, 0, st>>>(z_idx, mu_idx, B, C, w.mcnt,
+                                                                                        w.mlist);
+      EXVAE_CUDA(cudaGetLastError());
+    }
+    PriorTcArgs a{};
+    a.zp = w.zp; a.mp = w.mp; a.Bpad = w.Bpad; a.Cpad = w.Cpad; a.KP = w.KP; a.B = B; a.C = C;
+    a.mcnt = mask ? w.mcnt : nullptr; a.mlist = w.mlist; a.cidx = w.cidx; a.z_idx = z_idx; a.part = w.part;
+    int nsplit_tc = 0;
+    rc = prior_fwd_tc_launch(a, &nsplit_tc, st);
+    if (rc) return rc;
+    lse_merge_kernel<false><<<ceil_div(B, 8), 256, 0, st>>>(w.part, nsplit_tc, (size_t)nsplit_tc * 4, 4, B, nullptr,
+                                                            nullptr, D, 0.f, stats, nullptr, nullptr);
+    EXVAE_RETURN_LAST_ERROR();
+  }
   const FwdSmem L = fwd_smem_layout(w.LD);
   dim3 grid(w.nsplit, w.Bpad / PR_BM);
   if (mask) {
