@@ -299,28 +299,29 @@ struct AdamRec {
   float* v;
   long long n;
 };
-// one CTA per tensor: ||g||_2 (deterministic tree), CTA 0 also bumps the step counter
-__global__ void __launch_bounds__(1024) adam_norm_kernel(const AdamRec* __restrict__ table, float* __restrict__ norms,
-                                                         int64_t* __restrict__ step) {
-  __shared__ float sh[32];
+// ||g||_2^2 partials: grid = (tensors, ADAM_NCH chunks), deterministic tree per chunk; block (0,0) also
+// bumps the step counter.  The update kernel adds the ADAM_NCH partials in a fixed order.
+constexpr int ADAM_NCH = 16;
+__global__ void __launch_bounds__(256) adam_norm_kernel(const AdamRec* __restrict__ table, float* __restrict__ norms,
+                                                        int64_t* __restrict__ step) {
+  __shared__ float sh[8];
   const AdamRec rec = table[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float a = 0.f;
   if (rec.g)
-    for (long long e = tid; e < rec.n; e += blockDim.x) {
+    for (long long e = (long long)blockIdx.y * blockDim.x + tid; e < rec.n; e += (long long)ADAM_NCH * blockDim.x) {
       const float g = rec.g[e];
       a = fmaf(g, g, a);
     }
   a = warp_sum(a);
   if (lane == 0) sh[warp] = a;
   __syncthreads();
-  if (warp == 0) {
-    a = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.f;
-    a = warp_sum(a);
-    if (lane == 0) {
-      norms[blockIdx.x] = sqrtf(a);
-      if (blockIdx.x == 0) step[0] += 1;
-    }
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    norms[blockIdx.x * ADAM_NCH + blockIdx.y] = t;
+    if (blockIdx.x == 0 && blockIdx.y == 0) step[0] += 1;
   }
 }
 __global__ void __launch_bounds__(256) adam_update_kernel(const AdamRec* __restrict__ table,
@@ -334,7 +335,10 @@ __global__ void __launch_bounds__(256) adam_update_kernel(const AdamRec* __restr
   const double t = (double)step[0];
   const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
   const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-  const float inv = 1.f / (norms[blockIdx.y] + 1e-7f);
+  float nsq = 0.f;
+#pragma unroll
+  for (int i = 0; i < ADAM_NCH; ++i) nsq += norms[blockIdx.y * ADAM_NCH + i];
+  const float inv = 1.f / (sqrtf(nsq) + 1e-7f);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long e = base + (long long)j * blockDim.x + threadIdx.x;
@@ -471,7 +475,7 @@ extern "C" int exvae_adam_normgrad_step(const int64_t* table, int n_tensors, int
   static_assert(sizeof(AdamRec) == 5 * sizeof(int64_t), "table record is 5 x int64");
   cudaStream_t st = as_stream(stream);
   const AdamRec* recs = reinterpret_cast<const AdamRec*>(table);
-  adam_norm_kernel<<<n_tensors, 1024, 0, st>>>(recs, norms, step);
+  adam_norm_kernel<<<dim3(n_tensors, ADAM_NCH), 256, 0, st>>>(recs, norms, step);
   EXVAE_CUDA(cudaGetLastError());
   dim3 grid((unsigned)((max_numel + 1023) / 1024), n_tensors);
   adam_update_kernel<<<grid, 256, 0, st>>>(recs, norms, step, lr, beta1, beta2, eps, weight_decay);

@@ -321,6 +321,72 @@ __global__ void __launch_bounds__(256) act_dpre_kernel(const float* __restrict__
   }
 }
 
+// Tensor-core backward staging, ONE pass: pre-activation gradient -> hi/lo tf32 planes (the GEMM operands)
+// + per-row-chunk column sums (bias gradients).  Replaces dpre + split + column-sum (3 kernels, 2 extra
+// round trips through HBM).  Thread t owns columns t, t+256, ...: its sums need no cross-thread reduction.
+//   MODE 0: gated   dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*h*sig*(1-sig)        (ncat = 2*O)
+//   MODE 1: linear  dcat[r, j] = dout * act'(out)                                      (ncat = O)
+template <int MODE>
+__global__ void __launch_bounds__(256) dpre_split_colsum_kernel(const float* __restrict__ dout,
+                                                                const float* __restrict__ h,
+                                                                const float* __restrict__ sig_or_out, int R, int O,
+                                                                int act, float lo, float hi, int rows_per,
+                                                                float* __restrict__ dsplit,
+                                                                float* __restrict__ cs_part) {
+  constexpr int MAXJ = 4;                        // O <= 1024
+  const int ncat = MODE == 0 ? 2 * O : O;
+  const size_t plane = (size_t)R * ncat;
+  const int r0 = blockIdx.x * rows_per, r1 = min(R, r0 + rows_per);
+  float a0[MAXJ], a1[MAXJ];
+#pragma unroll
+  for (int q = 0; q < MAXJ; ++q) a0[q] = a1[q] = 0.f;
+  auto put = [&](size_t idx, float x) {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+    const float hf = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - hf));
+    dsplit[idx] = hf;
+    dsplit[plane + idx] = __uint_as_float(lb);
+  };
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int q = 0; q < MAXJ; ++q) {
+      const int j = threadIdx.x + 256 * q;
+      if (j < O) {
+        const size_t e = (size_t)r * O + j;
+        const float d = dout[e];
+        if (MODE == 0) {
+          const float s = sig_or_out[e], hv = h[e];
+          const float dh = d * s, dg = d * hv * s * (1.f - s);
+          put((size_t)r * ncat + j, dh);
+          put((size_t)r * ncat + O + j, dg);
+          a0[q] += dh;
+          a1[q] += dg;
+        } else {
+          float g = d;
+          if (act != EXVAE_ACT_NONE) {
+            const float o = sig_or_out[e];
+            if (act == EXVAE_ACT_SIGMOID) g *= o * (1.f - o);
+            else if (act == EXVAE_ACT_HARDTANH) g = (o > lo && o < hi) ? g : 0.f;
+            else if (act == EXVAE_ACT_RELU) g = o > 0.f ? g : 0.f;
+          }
+          put((size_t)r * ncat + j, g);
+          a0[q] += g;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MAXJ; ++q) {
+    const int j = threadIdx.x + 256 * q;
+    if (j < O) {
+      cs_part[(size_t)blockIdx.x * ncat + j] = a0[q];
+      if (MODE == 0) cs_part[(size_t)blockIdx.x * ncat + O + j] = a1[q];
+    }
+  }
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline int ew_blocks(long long n) { return (int)std::min<long long>((n + 255) / 256, 148LL * 16); }
 
@@ -413,11 +479,11 @@ inline FwdWs fwd_ws_layout(int R, int K, int OC) {
   return f;
 }
 inline bool tc_ok(int R, int K, int OC, const void* x) {
-  return tc_enabled() && tc_dims_ok(K) && tc_dims_ok(OC) && al16(x) && R > 0;
+  return tc_enabled() && tc_dims_ok(K) && tc_dims_ok(OC) && OC <= 2048 && al16(x) && R > 0;
 }
 struct TcBwdPlan {
-  int S, kchunk, S2, rows_per;
-  size_t off_dcat, off_dsplit, off_x, off_w, off_part, off_cs, bytes;
+  int S, kchunk, S2, rows_per, S3, rows_per3;
+  size_t off_dcat, off_dsplit, off_x, off_w, off_part, off_cs, off_cs3, bytes;
 };
 inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   TcBwdPlan b;
@@ -429,16 +495,19 @@ inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   S = std::max(1, std::min(S, ceil_div(R, 128)));
   b.kchunk = ceil_div(ceil_div(R, S), 32) * 32;
   b.S = ceil_div(R, b.kchunk);
-  b.S2 = std::max(1, std::min(64, ceil_div(R, 256)));
-  b.rows_per = ceil_div(R, b.S2);
+  b.rows_per = 16;                       // rows per staging block: enough blocks to saturate HBM
+  b.S2 = ceil_div(R, b.rows_per);
+  b.S3 = std::min(8, b.S2);              // second-level column-sum partials
+  b.rows_per3 = ceil_div(b.S2, b.S3);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  b.off_dcat = take(sizeof(float) * (size_t)R * ncat);
+  b.off_dcat = 0;
   b.off_dsplit = take(sizeof(float) * 2 * (size_t)R * ncat);
   b.off_x = take(sizeof(float) * 2 * (size_t)R * K);
   b.off_w = take(sizeof(float) * 2 * (size_t)ncat * K);
   b.off_part = take(sizeof(float) * (size_t)b.S * ncat * K);
   b.off_cs = take(sizeof(float) * (size_t)b.S2 * ncat);
+  b.off_cs3 = take(sizeof(float) * (size_t)b.S3 * ncat);
   b.bytes = off;
   return b;
 }
@@ -455,13 +524,13 @@ int tc_stage_operands(const float* x, const float* W0, const float* W1, int R, i
   return rc;
 }
 
-// dx / dW / db on the tensor cores.  dcat [R,ncat] fp32 is the pre-activation gradient.
-int dense_bwd_tc(const float* x, const float* W0, const float* W1, const float* dcat, int R, int K, int ncat, int oseg,
+// dx / dW / db on the tensor cores.  The pre-activation gradient arrives already staged by
+// dpre_split_colsum_kernel: hi/lo planes in ws+off_dsplit, column-sum partials in ws+off_cs.
+int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K, int ncat, int oseg,
                  float* dx, float* dW0, float* dW1, float* db0, float* db1, const float* xs_in, const float* ws_in,
                  const TcBwdPlan& plan, char* ws, int accumulate, cudaStream_t st) {
   float* dsplit = reinterpret_cast<float*>(ws + plan.off_dsplit);
-  int rc = tc_split(dcat, (size_t)R * ncat, dsplit, (size_t)R * ncat, st);
-  if (rc) return rc;
+  int rc;
   const float* xs = xs_in;
   const float* wsp = ws_in;
   if (!xs) {
@@ -493,12 +562,13 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, const float* 
                                                                          dW1 ? dW1 : dW0, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
-  if (db0 || db1) {
+  if (db0 || db1) {   // reduce the staging blocks' column sums: [S2, ncat] -> [S3, ncat] -> bias gradients
     float* cs = reinterpret_cast<float*>(ws + plan.off_cs);
-    dim3 g1(ceil_div(ncat, 32), plan.S2);
-    colsum_partial_kernel<<<g1, 256, 0, st>>>(dcat, R, ncat, plan.rows_per, cs);
+    float* cs3 = reinterpret_cast<float*>(ws + plan.off_cs3);
+    dim3 g1(ceil_div(ncat, 32), plan.S3);
+    colsum_partial_kernel<<<g1, 256, 0, st>>>(cs, plan.S2, ncat, plan.rows_per3, cs3);
     EXVAE_CUDA(cudaGetLastError());
-    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs, plan.S2, ncat, oseg, db0, db1, accumulate);
+    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs3, plan.S3, ncat, oseg, db0, db1, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
   return EXVAE_OK;
@@ -557,14 +627,15 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
   if (tc) {
     const TcBwdPlan plan = tc_bwd_plan(R, K, 2 * O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
-    float* dcat = reinterpret_cast<float*>(w + plan.off_dcat);
-    gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, h_lin, sig, R, O, dcat);
+    dpre_split_colsum_kernel<0><<<plan.S2, 256, 0, st>>>(dout, h_lin, sig, R, O, 0, 0.f, 0.f, plan.rows_per,
+                                                         reinterpret_cast<float*>(w + plan.off_dsplit),
+                                                         reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());
     const FwdWs f = fwd_ws_layout(R, K, 2 * O);
     const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
     const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
     const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
-    return dense_bwd_tc(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, xs, wsp, plan, w, accumulate, st);
+    return dense_bwd_tc(x, Wh, Wg, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, xs, wsp, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
   if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
@@ -614,22 +685,19 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
   EXVAE_CHECK_ARG(act == EXVAE_ACT_NONE || out != nullptr);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
-  const bool tc = tc_ok(R, K, O, x) && al16(W) && al16(ws) && al16(dout);
+  const bool tc = tc_ok(R, K, O, x) && O <= 1024 && al16(W) && al16(ws) && al16(dout);
   if (tc) {
     const TcBwdPlan plan = tc_bwd_plan(R, K, O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
-    const float* dpre = dout;
-    if (act != EXVAE_ACT_NONE) {
-      float* buf = reinterpret_cast<float*>(w + plan.off_dcat);
-      act_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, out, (long long)R * O, act, lo, hi, buf);
-      EXVAE_CUDA(cudaGetLastError());
-      dpre = buf;
-    }
+    dpre_split_colsum_kernel<1><<<plan.S2, 256, 0, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.rows_per,
+                                                         reinterpret_cast<float*>(w + plan.off_dsplit),
+                                                         reinterpret_cast<float*>(w + plan.off_cs));
+    EXVAE_CUDA(cudaGetLastError());
     const FwdWs f = fwd_ws_layout(R, K, O);
     const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
     const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
     const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
-    return dense_bwd_tc(x, W, nullptr, dpre, R, K, O, O, dx, dW, nullptr, db, nullptr, xs, wsp, plan, w, accumulate, st);
+    return dense_bwd_tc(x, W, nullptr, R, K, O, O, dx, dW, nullptr, db, nullptr, xs, wsp, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, O, true);
   if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
