@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
@@ -45,7 +47,9 @@ struct TcParams {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// CL = thread-block cluster size along the M tiles: the CL CTAs of a cluster compute different row blocks of
+// the SAME column tile, so each loads only 1/CL of the B tile and TMA-multicasts it to its peers.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(TTHREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   constexpr int A_BYTES = TBM * TBK * 4;   // 16 KB per plane
@@ -67,11 +71,13 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   const int kend = min(p.K, kbeg + p.kchunk);
   const int nkb = (kend - kbeg + TBK - 1) / TBK;
 
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < TSTAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);      // every CTA of the cluster must have consumed the stage before it is refilled
     }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
@@ -79,6 +85,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   if (warp == 1) tmem_alloc(tmem_slot, BN);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();    // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -101,17 +108,32 @@ __global__ void __launch_bounds__(TTHREADS, 1)
               tma_load_3d(sa + c * 4096, &tmA, &full[s], m0 + 32 * c, k0, pl);
           }
           unsigned char* sb = st + 2 * A_BYTES + pl * B_BYTES;
-          if (!B_MN) {
-            if (EPI == TC_GATED) {                                           // box {32 k, BN/2 rows}
-              tma_load_3d(sb, &tmB, &full[s], k0, n0, pl);
-              tma_load_3d(sb + (BN / 2) * 128, &tmB, &full[s], k0, p.gated_O + n0, pl);
+          if (CL == 1) {
+            if (!B_MN) {
+              if (EPI == TC_GATED) {                                           // box {32 k, BN/2 rows}
+                tma_load_3d(sb, &tmB, &full[s], k0, n0, pl);
+                tma_load_3d(sb + (BN / 2) * 128, &tmB, &full[s], k0, p.gated_O + n0, pl);
+              } else {
+                tma_load_3d(sb, &tmB, &full[s], k0, n0, pl);                  // box {32 k, BN rows}
+              }
             } else {
-              tma_load_3d(sb, &tmB, &full[s], k0, n0, pl);                  // box {32 k, BN rows}
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c)                                // box {32 n, 32 k}
+                tma_load_3d(sb + c * 4096, &tmB, &full[s], n0 + 32 * c, k0, pl);
             }
           } else {
+            // this CTA's 1/CL share of the B tile, multicast to the whole cluster
+            constexpr int SHARE = BN / CL;                                     // rows (K-major) or columns (MN-major)
+            const int r0 = crank * SHARE;                                      // first tile row/column of the share
+            if (!B_MN) {                                                       // box {32 k, SHARE rows}
+              int grow = n0 + r0;
+              if (EPI == TC_GATED) grow = (r0 < BN / 2) ? n0 + r0 : p.gated_O + n0 + (r0 - BN / 2);
+              tma_load_3d_mc(sb + r0 * 128, &tmB, &full[s], k0, grow, pl, cmask);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c)                                // box {32 n, 32 k}
-              tma_load_3d(sb + c * 4096, &tmB, &full[s], n0 + 32 * c, k0, pl);
+              for (int c = 0; c < SHARE / 32; ++c)                             // box {32 n, 32 k}
+                tma_load_3d_mc(sb + (r0 / 32 + c) * 4096, &tmB, &full[s], n0 + r0 + 32 * c, k0, pl, cmask);
+            }
           }
         }
       }
@@ -142,7 +164,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
           umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
         }
-        umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+        // frees the stage (in every CTA of the cluster) once these MMAs have read it
+        if (CL == 1) umma_commit(&empty[s]);
+        else umma_commit_mc(&empty[s], cmask);
       }
       umma_commit(tmem_full);     // accumulator complete
     }
@@ -243,6 +267,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();    // no CTA exits while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
@@ -279,21 +304,42 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+int launch_cl(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE = 2 * TBM * TBK * 4 + 2 * BN * TBK * 4;
   constexpr int SMEM = TSTAGES * STAGE + 1024 + 256;
-  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
   if (!configured) {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  dim3 grid(EPI == TC_GATED ? ceil_div(g.gated_O, BN / 2) : ceil_div(g.N, BN), ceil_div(g.M, TBM),
+  const int mtiles = ceil_div(g.M, TBM);
+  dim3 grid(EPI == TC_GATED ? ceil_div(g.gated_O, BN / 2) : ceil_div(g.N, BN), ceil_div(mtiles, CL) * CL,
             EPI == TC_SPLITK ? g.splits : 1);
-  kern<<<grid, TTHREADS, SMEM, st>>>(ma, mb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TTHREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CL;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
   return e == cudaSuccess ? EXVAE_OK : (int)e;
+}
+
+// cluster size along M: 4 when the row blocks allow it (B-tile traffic / 4), never for split-K (odd tile counts)
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch(const TcGemm& g, const CUtensorMap (&mb)[3], const CUtensorMap& ma, const TcParams& p, int cl,
+           cudaStream_t st) {
+  if (cl == 4) return launch_cl<BN, A_MN, B_MN, EPI, 4>(g, ma, mb[2], p, st);
+  if (cl == 2) return launch_cl<BN, A_MN, B_MN, EPI, 2>(g, ma, mb[1], p, st);
+  return launch_cl<BN, A_MN, B_MN, EPI, 1>(g, ma, mb[0], p, st);
 }
 
 }  // namespace
@@ -326,13 +372,32 @@ int tc_split(const float* x, size_t n, float* out, size_t plane_stride, cudaStre
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
 
+int tc_cluster_size(const TcGemm& g) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* env = getenv("EXVAE_GEMM_CLUSTER");
+    forced = env ? atoi(env) : 0;
+  }
+  // Measured on B200 (profiles/r1_gemm_multicast.md): multicasting the B tile over 2 or 4 CTAs does NOT speed
+  // the GEMMs up (1.72 / 1.72 / 1.78 ms per step for cluster 1 / 2 / 4): the limiter is the ~40 B/clk each SM can
+  // ingest, not the L2 read traffic, and every CTA still receives the full tile.  Default: no cluster.
+  if (g.epi == TC_SPLITK || forced <= 1) return 1;
+  const int mtiles = ceil_div(g.M, TBM);
+  int cl = (mtiles % 4 == 0) ? 4 : (mtiles % 2 == 0) ? 2 : 1;
+  return std::min(cl, forced);
+}
+
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   constexpr int BN = 128;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb[3];
   int rc = make_map(&ma, g.a_split, g.a_rows, g.a_cols, g.a_mn ? 32 : TBM, g.a_mn);
   if (rc) return rc;
-  const int b_box = g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN);
-  rc = make_map(&mb, g.b_split, g.b_rows, g.b_cols, b_box, g.b_mn);
+  const int cl = tc_cluster_size(g);
+  // B box rows: whole tile (gated: one half) without clusters, the CTA's 1/cl share with multicast
+  const int b_box1 = g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN);
+  const int idx = cl == 4 ? 2 : cl == 2 ? 1 : 0;
+  const int b_box = cl == 1 ? b_box1 : (g.b_mn ? 32 : BN / cl);
+  rc = make_map(&mb[idx], g.b_split, g.b_rows, g.b_cols, b_box, g.b_mn);
   if (rc) return rc;
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
@@ -343,10 +408,10 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.c_vec = (g.ldc % 4 == 0) && al16(g.out0) && (!g.out1 || al16(g.out1)) && (!g.out2 || al16(g.out2)) &&
             (g.epi != TC_SPLITK || ((size_t)g.M * g.ldc) % 4 == 0);
-  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, p, st);
-  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, p, st);
-  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, p, st);
-  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, ma, mb, p, st);
+  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, mb, ma, p, cl, st);
+  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, mb, ma, p, cl, st);
+  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, mb, ma, p, cl, st);
+  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, mb, ma, p, cl, st);
   return EXVAE_ERR_UNSUPPORTED;
 }
 
