@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(256) gated_dpre_kernel(const float* __restrict
        e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / O;
     const int j = (int)(e - r * O);
-    const float d = dout[e], s = sig[e], hv = h[e];
+    const float d = dout[e], s = sig[e], ov = h[e];   // ov = layer output h*s
     dcat[r * 2 * O + j] = d * s;
-    dcat[r * 2 * O + O + j] = d * hv * s * (1.f - s);
+    dcat[r * 2 * O + O + j] = d * ov * (1.f - s);
   }
 }
 // dpre = dout * act'(out)
@@ -321,13 +321,13 @@ __global__ void __launch_bounds__(256) act_dpre_kernel(const float* __restrict__
   }
 }
 
-// Tensor-core backward staging, ONE pass: pre-activation gradient -> hi/lo tf32 planes (the GEMM operands)
-// + per-row-chunk column sums (bias gradients).  Replaces dpre + split + column-sum (3 kernels, 2 extra
-// round trips through HBM).  Thread t owns columns t, t+256, ...: its sums need no cross-thread reduction.
-//   MODE 0: gated   dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*h*sig*(1-sig)        (ncat = 2*O)
+// Tensor-core backward staging, ONE pass: pre-activation gradient dcat (the fp32 GEMM operand; the GEMM splits it
+// into tf32 hi/lo parts in shared memory) + per-row-chunk column sums (bias gradients).  Replaces dpre + column-sum
+// (2 kernels, 1 extra round trip through HBM).  Thread t owns columns t, t+256, ...: its sums need no cross-thread reduction.
+//   MODE 0: gated   dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*out*(1-sig), out = h*sig   (ncat = 2*O)
 //   MODE 1: linear  dcat[r, j] = dout * act'(out)                                      (ncat = O)
 template <int MODE>
-__global__ void __launch_bounds__(256) dpre_split_colsum_kernel(const float* __restrict__ dout,
+__global__ void __launch_bounds__(256) dpre_colsum_kernel(const float* __restrict__ dout,
                                                                 const float* __restrict__ h,
                                                                 const float* __restrict__ sig_or_out, int R, int O,
                                                                 int act, float lo, float hi, int rows_per,
@@ -335,19 +335,11 @@ __global__ void __launch_bounds__(256) dpre_split_colsum_kernel(const float* __r
                                                                 float* __restrict__ cs_part) {
   constexpr int MAXJ = 4;                        // O <= 1024
   const int ncat = MODE == 0 ? 2 * O : O;
-  const size_t plane = (size_t)R * ncat;
   const int r0 = blockIdx.x * rows_per, r1 = min(R, r0 + rows_per);
   float a0[MAXJ], a1[MAXJ];
 #pragma unroll
   for (int q = 0; q < MAXJ; ++q) a0[q] = a1[q] = 0.f;
-  auto put = [&](size_t idx, float x) {
-    uint32_t hb, lb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-    const float hf = __uint_as_float(hb);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - hf));
-    dsplit[idx] = hf;
-    dsplit[plane + idx] = __uint_as_float(lb);
-  };
+  auto put = [&](size_t idx, float x) { dsplit[idx] = x; };
 #pragma unroll 4
   for (int r = r0; r < r1; ++r) {
 #pragma unroll
@@ -357,8 +349,8 @@ __global__ void __launch_bounds__(256) dpre_split_colsum_kernel(const float* __r
         const size_t e = (size_t)r * O + j;
         const float d = dout[e];
         if (MODE == 0) {
-          const float s = sig_or_out[e], hv = h[e];
-          const float dh = d * s, dg = d * hv * s * (1.f - s);
+          const float s = sig_or_out[e], ov = h[e];   // ov = layer output h*s
+          const float dh = d * s, dg = d * ov * (1.f - s);
           put((size_t)r * ncat + j, dh);
           put((size_t)r * ncat + O + j, dg);
           a0[q] += dh;
@@ -466,16 +458,16 @@ int dense_bwd_common(const float* x, const float* W0, const float* W1, const flo
 }
 
 // ------------------------------------------------------------------ tensor-core (3xTF32) plumbing
-// forward workspace: [x_split 2*R*K][w_split 2*OC*K]  (OC = 2*O gated, O linear); kept by the caller
-// for the backward so operands are split once per step.
+// forward workspace: gated layers keep [Wh ; Wg] concatenated as one [2*O, K] operand (reused by the backward);
+// plain linear layers need none (the GEMM reads x and W where they lie).
 struct FwdWs {
-  size_t off_x, off_w, bytes;
+  size_t off_w, bytes;
 };
-inline FwdWs fwd_ws_layout(int R, int K, int OC) {
+inline FwdWs fwd_ws_layout(int R, int K, int OC, bool gated) {
+  (void)R;
   FwdWs f;
-  f.off_x = 0;
-  f.off_w = align_up(sizeof(float) * 2 * (size_t)R * K, 256);
-  f.bytes = f.off_w + align_up(sizeof(float) * 2 * (size_t)OC * K, 256);
+  f.off_w = 0;
+  f.bytes = gated ? align_up(sizeof(float) * (size_t)OC * K, 256) : 0;
   return f;
 }
 inline bool tc_ok(int R, int K, int OC, const void* x) {
@@ -483,7 +475,7 @@ inline bool tc_ok(int R, int K, int OC, const void* x) {
 }
 struct TcBwdPlan {
   int S, kchunk, S2, rows_per, S3, rows_per3;
-  size_t off_dcat, off_dsplit, off_x, off_w, off_part, off_cs, off_cs3, bytes;
+  size_t off_dcat, off_dsplit, off_w, off_part, off_cs, off_cs3, bytes;
 };
 inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   TcBwdPlan b;
@@ -502,9 +494,8 @@ inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   b.off_dcat = 0;
-  b.off_dsplit = take(sizeof(float) * 2 * (size_t)R * ncat);
-  b.off_x = take(sizeof(float) * 2 * (size_t)R * K);
-  b.off_w = take(sizeof(float) * 2 * (size_t)ncat * K);
+  b.off_dsplit = take(sizeof(float) * (size_t)R * ncat);
+  b.off_w = take(sizeof(float) * (size_t)ncat * K);
   b.off_part = take(sizeof(float) * (size_t)b.S * ncat * K);
   b.off_cs = take(sizeof(float) * (size_t)b.S2 * ncat);
   b.off_cs3 = take(sizeof(float) * (size_t)b.S3 * ncat);
@@ -512,48 +503,33 @@ inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   return b;
 }
 
-// split x [R,K] and the (one or two segment) weights [OC,K] into hi/lo planes
-int tc_stage_operands(const float* x, const float* W0, const float* W1, int R, int K, int O, float* xs, float* wsplit,
-                      cudaStream_t st) {
-  int rc = tc_split(x, (size_t)R * K, xs, (size_t)R * K, st);
-  if (rc) return rc;
-  const int OC = W1 ? 2 * O : O;
-  rc = tc_split(W0, (size_t)O * K, wsplit, (size_t)OC * K, st);
-  if (rc) return rc;
-  if (W1) rc = tc_split(W1, (size_t)O * K, wsplit + (size_t)O * K, (size_t)OC * K, st);
-  return rc;
-}
-
-// dx / dW / db on the tensor cores.  The pre-activation gradient arrives already staged by
-// dpre_split_colsum_kernel: hi/lo planes in ws+off_dsplit, column-sum partials in ws+off_cs.
+// dx / dW / db on the tensor cores.  The pre-activation gradient arrives already staged by dpre_colsum_kernel:
+// dcat in ws+off_dsplit, column-sum partials in ws+off_cs.  wcat_in: the forward's [W0 ; W1] copy (gated) or null.
 int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K, int ncat, int oseg,
-                 float* dx, float* dW0, float* dW1, float* db0, float* db1, const float* xs_in, const float* ws_in,
+                 float* dx, float* dW0, float* dW1, float* db0, float* db1, const float* wcat_in,
                  const TcBwdPlan& plan, char* ws, int accumulate, cudaStream_t st) {
   float* dsplit = reinterpret_cast<float*>(ws + plan.off_dsplit);
   int rc;
-  const float* xs = xs_in;
-  const float* wsp = ws_in;
-  if (!xs) {
-    float* xs_own = reinterpret_cast<float*>(ws + plan.off_x);
+  const float* wsp = W1 ? wcat_in : W0;
+  if (dx && !wsp) {
     float* w_own = reinterpret_cast<float*>(ws + plan.off_w);
-    rc = tc_stage_operands(x, W0, W1, R, K, W1 ? oseg : ncat, xs_own, w_own, st);
+    rc = tc_concat2(W0, W1, (size_t)oseg * K, w_own, st);
     if (rc) return rc;
-    xs = xs_own;
     wsp = w_own;
   }
   if (dx) {  // dx[R,K] = dcat[R,ncat] . Wcat[ncat,K]  : A K-major, B MN-major (planes [ncat rows][K cols])
     TcGemm g{};
-    g.a_split = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = false;
-    g.b_split = wsp; g.b_rows = ncat; g.b_cols = K; g.b_mn = true;
+    g.a = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = false;
+    g.b = wsp; g.b_rows = ncat; g.b_cols = K; g.b_mn = true;
     g.M = R; g.N = K; g.K = ncat; g.epi = TC_PLAIN; g.out0 = dx; g.ldc = K;
     rc = tc_gemm_launch(g, st);
     if (rc) return rc;
   }
-  {  // dWcat[ncat,K] = dcat^T . x : A MN-major (planes [R rows][ncat cols]), B MN-major (planes [R rows][K cols])
+  {  // dWcat[ncat,K] = dcat^T . x : A MN-major ([R rows][ncat cols]), B MN-major ([R rows][K cols])
     float* part = reinterpret_cast<float*>(ws + plan.off_part);
     TcGemm g{};
-    g.a_split = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = true;
-    g.b_split = xs; g.b_rows = R; g.b_cols = K; g.b_mn = true;
+    g.a = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = true;
+    g.b = x; g.b_rows = R; g.b_cols = K; g.b_mn = true;
     g.M = ncat; g.N = K; g.K = R; g.epi = TC_SPLITK; g.out0 = part; g.ldc = K;
     g.splits = plan.S; g.kchunk = plan.kchunk;
     rc = tc_gemm_launch(g, st);
@@ -581,33 +557,32 @@ using namespace exvae;
 
 extern "C" size_t exvae_dense_fwd_workspace_bytes(int R, int K, int O, int gated) {
   if (R <= 0 || K <= 0 || O <= 0) return 0;
-  return fwd_ws_layout(R, K, gated ? 2 * O : O).bytes;
+  return fwd_ws_layout(R, K, gated ? 2 * O : O, gated != 0).bytes;
 }
 
 extern "C" int exvae_gated_dense_fwd(const float* x, const float* Wh, const float* bh, const float* Wg, const float* bg,
-                                     int R, int K, int O, float* out, float* h_lin, float* sig, void* ws,
+                                     int R, int K, int O, float* out, float* sig, void* ws,
                                      size_t ws_bytes, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && Wh && Wg && out && R > 0 && K > 0 && O > 0);
   cudaStream_t st = as_stream(stream);
-  const FwdWs f = fwd_ws_layout(R, K, 2 * O);
+  const FwdWs f = fwd_ws_layout(R, K, 2 * O, true);
   if (ws && ws_bytes >= f.bytes && tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws)) {
-    float* xs = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_x);
     float* wsp = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_w);
-    int rc = tc_stage_operands(x, Wh, Wg, R, K, O, xs, wsp, st);
+    int rc = tc_concat2(Wh, Wg, (size_t)O * K, wsp, st);
     if (rc) return rc;
     TcGemm g{};
-    g.a_split = xs; g.a_rows = R; g.a_cols = K; g.a_mn = false;
-    g.b_split = wsp; g.b_rows = 2 * O; g.b_cols = K; g.b_mn = false;
+    g.a = x; g.a_rows = R; g.a_cols = K; g.a_mn = false;
+    g.b = wsp; g.b_rows = 2 * O; g.b_cols = K; g.b_mn = false;
     g.M = R; g.N = O; g.K = K; g.epi = TC_GATED; g.gated_O = O;
-    g.bias0 = bh; g.bias1 = bg; g.out0 = out; g.out1 = h_lin; g.out2 = sig; g.ldc = O;
+    g.bias0 = bh; g.bias1 = bg; g.out0 = out; g.out1 = nullptr; g.out2 = sig; g.ldc = O;
     return tc_gemm_launch(g, st);
   }
   GemmP p{};
   p.A = x; p.lda = K; p.B0 = Wh; p.B1 = Wg; p.ldb = K; p.M = R; p.N = 2 * O; p.K = K; p.kchunk = K;
-  p.bias0 = bh; p.bias1 = bg; p.out0 = out; p.out1 = h_lin; p.out2 = sig; p.ldc = O; p.O = O;
+  p.bias0 = bh; p.bias1 = bg; p.out0 = out; p.out1 = nullptr; p.out2 = sig; p.ldc = O; p.O = O;
   p.a_vec = (K % 4 == 0) && al16(x);
   p.b_vec = (K % 4 == 0) && al16(Wh) && al16(Wg);
-  p.c_vec = (O % 4 == 0) && al16(out) && (!h_lin || al16(h_lin)) && (!sig || al16(sig));
+  p.c_vec = (O % 4 == 0) && al16(out) && (!sig || al16(sig));
   return launch_gemm<L_KC, L_KC, EPI_GATED>(p, 1, st);
 }
 
@@ -616,31 +591,30 @@ extern "C" size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O) {
   return std::max(bwd_plan(R, K, 2 * O, true).bytes, tc_bwd_plan(R, K, 2 * O).bytes);
 }
 
-extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin,
+extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* out,
                                      const float* sig, const float* dout, int R, int K, int O, float* dx, float* dWh,
                                      float* dbh, float* dWg, float* dbg, const void* fwd_ws, size_t fwd_ws_bytes,
                                      void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream) {
-  EXVAE_CHECK_ARG(x && Wh && Wg && h_lin && sig && dout && dWh && dWg && ws && R > 0 && K > 0 && O > 0);
+  EXVAE_CHECK_ARG(x && Wh && Wg && out && sig && dout && dWh && dWg && ws && R > 0 && K > 0 && O > 0);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
   const bool tc = tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws);
   if (tc) {
     const TcBwdPlan plan = tc_bwd_plan(R, K, 2 * O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
-    dpre_split_colsum_kernel<0><<<plan.S2, 256, 0, st>>>(dout, h_lin, sig, R, O, 0, 0.f, 0.f, plan.rows_per,
+    dpre_colsum_kernel<0><<<plan.S2, 256, 0, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, plan.rows_per,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
                                                          reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());
-    const FwdWs f = fwd_ws_layout(R, K, 2 * O);
-    const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
-    const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
+    const FwdWs f = fwd_ws_layout(R, K, 2 * O, true);
+    const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes && al16(fwd_ws);
     const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
-    return dense_bwd_tc(x, Wh, Wg, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, xs, wsp, plan, w, accumulate, st);
+    return dense_bwd_tc(x, Wh, Wg, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, wsp, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
   if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
   float* dcat = reinterpret_cast<float*>(w + plan.off_dcat);
-  gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, h_lin, sig, R, O, dcat);
+  gated_dpre_kernel<<<ew_blocks((long long)R * O), 256, 0, st>>>(dout, out, sig, R, O, dcat);
   EXVAE_CUDA(cudaGetLastError());
   return dense_bwd_common(x, Wh, Wg, dcat, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, plan, w, accumulate, st);
 }
@@ -650,15 +624,11 @@ extern "C" int exvae_linear_fwd(const float* x, const float* W, const float* b, 
   EXVAE_CHECK_ARG(x && W && out && R > 0 && K > 0 && O > 0);
   EXVAE_CHECK_ARG(act >= EXVAE_ACT_NONE && act <= EXVAE_ACT_RELU);
   cudaStream_t st = as_stream(stream);
-  const FwdWs f = fwd_ws_layout(R, K, O);
-  if (ws && ws_bytes >= f.bytes && tc_ok(R, K, O, x) && al16(W) && al16(ws)) {
-    float* xs = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_x);
-    float* wsp = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_w);
-    int rc = tc_stage_operands(x, W, nullptr, R, K, O, xs, wsp, st);
-    if (rc) return rc;
+  (void)ws; (void)ws_bytes;
+  if (tc_ok(R, K, O, x) && al16(W)) {
     TcGemm g{};
-    g.a_split = xs; g.a_rows = R; g.a_cols = K; g.a_mn = false;
-    g.b_split = wsp; g.b_rows = O; g.b_cols = K; g.b_mn = false;
+    g.a = x; g.a_rows = R; g.a_cols = K; g.a_mn = false;
+    g.b = W; g.b_rows = O; g.b_cols = K; g.b_mn = false;
     g.M = R; g.N = O; g.K = K; g.epi = TC_BIAS_ACT;
     g.bias0 = b; g.out0 = out; g.ldc = O; g.act = act; g.lo = lo; g.hi = hi;
     return tc_gemm_launch(g, st);
@@ -689,15 +659,12 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
   if (tc) {
     const TcBwdPlan plan = tc_bwd_plan(R, K, O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
-    dpre_split_colsum_kernel<1><<<plan.S2, 256, 0, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.rows_per,
+    dpre_colsum_kernel<1><<<plan.S2, 256, 0, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.rows_per,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
                                                          reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());
-    const FwdWs f = fwd_ws_layout(R, K, O);
-    const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes;
-    const float* xs = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_x) : nullptr;
-    const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
-    return dense_bwd_tc(x, W, nullptr, R, K, O, O, dx, dW, nullptr, db, nullptr, xs, wsp, plan, w, accumulate, st);
+    (void)fwd_ws; (void)fwd_ws_bytes;
+    return dense_bwd_tc(x, W, nullptr, R, K, O, O, dx, dW, nullptr, db, nullptr, nullptr, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, O, true);
   if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
@@ -712,3 +679,7 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
 }
 
 extern "C" int exvae_gemm_backend(void) { return tc_enabled() ? 1 : 0; }
+extern "C" int exvae_gemm_set_trace(uint64_t* buf) {
+  tc_set_trace(reinterpret_cast<unsigned long long*>(buf));
+  return EXVAE_OK;
+}

@@ -281,21 +281,20 @@ class _GatedDense(torch.autograd.Function):
         O = Wh.shape[0]
         out = torch.empty((R, O), dtype=torch.float32, device=x.device)
         need = any(ctx.needs_input_grad)
-        h = torch.empty_like(out) if need else None
         s = torch.empty_like(out) if need else None
-        # forward workspace = hi/lo operand splits of the tensor-core backend; kept for the backward
+        # forward workspace = [Wh ; Wg] as one GEMM operand of the tensor-core backend; kept for the backward
         fws = _ws(L.exvae_dense_fwd_workspace_bytes(R, K, O, 1), x.device)
-        L.check(L.exvae_gated_dense_fwd(_p(x), _p(Wh), _p(bh), _p(Wg), _p(bg), R, K, O, _p(out), _p(h), _p(s),
+        L.check(L.exvae_gated_dense_fwd(_p(x), _p(Wh), _p(bh), _p(Wg), _p(bg), R, K, O, _p(out), _p(s),
                                         _p(fws), fws.numel(), _stream()), "gated_dense_fwd")
-        _count(4)
-        ctx.save_for_backward(x, Wh, Wg, h, s, fws if need else None)
+        _count(2)
+        ctx.save_for_backward(x, Wh, Wg, out if need else None, s, fws if need else None)
         ctx.has_bias = (bh is not None, bg is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = lib()
-        x, Wh, Wg, h, s, fws = ctx.saved_tensors
+        x, Wh, Wg, out, s, fws = ctx.saved_tensors
         dout = _f32(dout)
         R, K = x.shape
         O = Wh.shape[0]
@@ -308,11 +307,11 @@ class _GatedDense(torch.autograd.Function):
             dbh = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
             dbg = torch.empty((O,), dtype=torch.float32, device=x.device) if ctx.has_bias[1] else None
         ws = _ws(L.exvae_gated_dense_bwd_workspace_bytes(R, K, O), x.device)
-        L.check(L.exvae_gated_dense_bwd(_p(x), _p(Wh), _p(Wg), _p(h), _p(s), _p(dout), R, K, O, _p(dx), _p(dWh),
+        L.check(L.exvae_gated_dense_bwd(_p(x), _p(Wh), _p(Wg), _p(out), _p(s), _p(dout), R, K, O, _p(dx), _p(dWh),
                                         _p(dbh), _p(dWg), _p(dbg), _p(fws), fws.numel() if fws is not None else 0,
                                         _p(ws), ws.numel(), 1 if sink is not None else 0, _stream()),
                 "gated_dense_bwd")
-        _count(6 + (1 if dx is not None else 0))
+        _count(5 + (1 if dx is not None else 0))
         if sink is not None:
             return dx, None, None, None, None, None
         return dx, dWh, dbh, dWg, dbg, None
@@ -365,7 +364,7 @@ class _Linear(torch.autograd.Function):
         fws = _ws(L.exvae_dense_fwd_workspace_bytes(R, K, O, 0), x.device)
         L.check(L.exvae_linear_fwd(_p(x), _p(W), _p(b), R, K, O, act, lo, hi, _p(out), _p(fws), fws.numel(),
                                    _stream()), "linear_fwd")
-        _count(3)
+        _count(1)
         ctx.save_for_backward(x, W, out if act != ACT_NONE else None, fws if any(ctx.needs_input_grad) else None)
         ctx.cfg = (act, lo, hi, b is not None)
         return out
@@ -389,7 +388,7 @@ class _Linear(torch.autograd.Function):
         L.check(L.exvae_linear_bwd(_p(x), _p(W), _p(out), _p(dout), R, K, O, act, lo, hi, _p(dx), _p(dW), _p(db),
                                    _p(fws), fws.numel() if fws is not None else 0, _p(ws), ws.numel(),
                                    1 if sink is not None else 0, _stream()), "linear_bwd")
-        _count(5 + (1 if dx is not None else 0) + (1 if act != ACT_NONE else 0))
+        _count(5 + (1 if dx is not None else 0))
         if sink is not None:
             return dx, None, None, None, None, None, None
         return dx, dW, db, None, None, None, None

@@ -124,20 +124,22 @@ EXVAE_API int exvae_scatter_rows(float* dst, const int64_t* idx, int n_rows, int
 
 /* ---------------------------------------------------------------- dense layers (K3)
  * GatedDense (utils/nn.py:44-69): out = (x Wh^T + bh) * sigmoid(x Wg^T + bg).
- * x [R,K], Wh/Wg [O,K], out [R,O].  h_lin/sig [R,O] are saved for the backward (NULL to skip).
+ * x [R,K], Wh/Wg [O,K], out [R,O].  sig [R,O] = sigmoid(x Wg^T + bg) is saved for the backward (NULL to
+ * skip); the backward needs only `out` and `sig`:  dh = dout*sig,  dg = dout*out*(1-sig).
  *
  * Backend: error-compensated 3xTF32 on the tcgen05 tensor cores when the shapes allow TMA (K and
  * the output width multiples of 4, 16-byte aligned pointers) and a forward workspace is given,
- * else the fp32 FMA-pipe GEMM (EXVAE_GEMM=simt forces the latter).  The forward workspace holds
- * the hi/lo operand splits; pass it to the backward (fwd_ws) to reuse them, or NULL.               */
+ * else the fp32 FMA-pipe GEMM (EXVAE_GEMM=simt forces the latter).  Operands stay plain fp32 in HBM (the
+ * kernel splits them into tf32 hi/lo parts in shared memory); the forward workspace of a gated layer holds
+ * [Wh ; Wg] as one operand: pass it to the backward (fwd_ws) to reuse it, or NULL.                  */
 EXVAE_API size_t exvae_dense_fwd_workspace_bytes(int R, int K, int O, int gated);
 EXVAE_API int exvae_gated_dense_fwd(const float* x, const float* Wh, const float* bh, const float* Wg, const float* bg, int R,
-                          int K, int O, float* out, float* h_lin, float* sig, void* ws, size_t ws_bytes,
+                          int K, int O, float* out, float* sig, void* ws, size_t ws_bytes,
                           exvae_stream_t stream);
 EXVAE_API size_t exvae_gated_dense_bwd_workspace_bytes(int R, int K, int O);
 /* dx may be NULL (first layer: the input is data).  accumulate=1: dW/db are ADDED into the given
  * buffers (fused gradient accumulation straight into the .grad storage) instead of overwritten. */
-EXVAE_API int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* h_lin, const float* sig,
+EXVAE_API int exvae_gated_dense_bwd(const float* x, const float* Wh, const float* Wg, const float* out, const float* sig,
                           const float* dout, int R, int K, int O, float* dx, float* dWh, float* dbh, float* dWg,
                           float* dbg, const void* fwd_ws, size_t fwd_ws_bytes, void* ws, size_t ws_bytes,
                           int accumulate, exvae_stream_t stream);
@@ -151,6 +153,10 @@ EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out,
                      void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream);
 /* 1 = tcgen05 3xTF32 backend active on the current device, 0 = fp32 FMA-pipe backend */
 EXVAE_API int exvae_gemm_backend(void);
+/* Debug / profiling aid (tools/gemm_trace.py): when buf != NULL every CTA of the following tensor-core GEMM
+ * launches writes 8 uint64 {globaltimer at start, clock64 at start, globaltimer after setup / at the first MMA / at
+ * accumulator complete, clock64 at end, globaltimer at end, SM id} at buf[8*linear_cta_index]; NULL switches tracing off. */
+EXVAE_API int exvae_gemm_set_trace(uint64_t* buf);
 
 /* ---------------------------------------------------------------- convolution support (K4)
  * GatedConv2d / Conv2d (utils/nn.py:72-114) and the weight-normed conv / ELU / Upsample blocks of

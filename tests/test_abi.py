@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(L):
 def test_argument_errors_without_gpu(L):
     # null pointers / non-positive sizes are rejected before any CUDA call
     assert L.exvae_pairwise_distance(None, None, 4, 4, 4, None, None) == -1
-    assert L.exvae_gated_dense_fwd(None, None, None, None, None, 1, 1, 1, None, None, None, None, 0, None) == -1
+    assert L.exvae_gated_dense_fwd(None, None, None, None, None, 1, 1, 1, None, None, None, 0, None) == -1
     assert L.exvae_prior_lse_workspace_bytes(0, 10, 40) == 0
     n = L.exvae_prior_lse_workspace_bytes(512, 25000, 40)
     assert 4e6 < n < 2e8

@@ -1,0 +1,55 @@
+"""Per-CTA phase trace of the tensor-core GEMM (run on a B200): where does a tile's time go?
+
+usage: python tools/gemm_trace.py [R K O]   (gated forward, then its backward)"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from exemplar_vae_b200 import ops  # noqa: E402
+from exemplar_vae_b200._lib import lib  # noqa: E402
+
+R, K, O = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (25512, 784, 300)
+g = torch.Generator().manual_seed(0)
+x = torch.randn(R, K, generator=g).cuda().requires_grad_(True)
+Wh = (torch.randn(O, K, generator=g) / K ** 0.5).cuda().requires_grad_(True)
+Wg = (torch.randn(O, K, generator=g) / K ** 0.5).cuda().requires_grad_(True)
+b = torch.zeros(O).cuda().requires_grad_(True)
+dout = torch.randn(R, O, generator=g).cuda()
+L = lib()
+
+
+def summarize(name, buf, ncta):
+    t = buf[: ncta * 8].cpu().numpy().astype(np.int64).reshape(ncta, 8)
+    t = t[t[:, 0] > 0]
+    span = (t[:, 6].max() - t[:, 0].min()) / 1e3
+    life = (t[:, 6] - t[:, 0]) / 1e3
+    print(f"{name}: {len(t)} persistent CTAs, kernel span {span:.1f} us; per CTA (median / max):")
+    print(f"   tiles per CTA                      {np.median(t[:, 2]):8.0f} {t[:, 2].max():8.0f}")
+    print(f"   CTA lifetime (us)                  {np.median(life):8.2f} {life.max():8.2f}")
+    print(f"   MMA warp waiting for converters    {np.median(t[:, 3]) / 1e3:8.2f} {t[:, 3].max() / 1e3:8.2f}")
+    print(f"   MMA warp waiting for accumulator   {np.median(t[:, 5]) / 1e3:8.2f} {t[:, 5].max() / 1e3:8.2f}")
+    print(f"   epilogue warp busy                 {np.median(t[:, 4]) / 1e3:8.2f} {t[:, 4].max() / 1e3:8.2f}")
+
+
+# bring the clocks up
+for _ in range(int(os.environ.get("WARM", "300"))):
+    out = ops.gated_dense(x, Wh, b, Wg, b)
+torch.cuda.synchronize()
+buf = torch.zeros(8 * 200000, dtype=torch.int64, device="cuda")
+L.exvae_gemm_set_trace(buf.data_ptr())
+out = ops.gated_dense(x, Wh, b, Wg, b)
+torch.cuda.synchronize()
+L.exvae_gemm_set_trace(None)
+summarize(f"gated fwd R={R} K={K} O={O}", buf, min(148, ((O + 63) // 64) * ((R + 127) // 128)))
+L.exvae_gemm_set_trace(buf.data_ptr())
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record()
+for _ in range(20):
+    out = ops.gated_dense(x, Wh, b, Wg, b)
+ev[1].record()
+torch.cuda.synchronize()
+L.exvae_gemm_set_trace(None)
+print("fwd entry point (debug mode %s): %.1f us per call" % (os.environ.get("EXVAE_GEMM_DEBUG", "0"), ev[0].elapsed_time(ev[1]) * 50))
