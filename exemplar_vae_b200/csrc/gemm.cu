@@ -479,12 +479,22 @@ struct TcBwdPlan {
 };
 inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   TcBwdPlan b;
+  // Split the reduction over the R rows so that the persistent kernel's tiles fill whole waves of SMs: cost (in
+  // k-blocks of 32 rows) = waves * k-blocks per split + the write/read of one more partial [ncat,K] per split
+  // (~3 TB/s against ~0.77 us per k-block).  Accuracy: the TMEM accumulator is fp32 with truncating adds, so one
+  // accumulation chain is capped at 2560 rows; the fp32 split-K reduction (round-to-nearest) combines the chunks.
   const int tiles = ceil_div(ncat, 128) * ceil_div(K, 128);
-  int S = std::max(1, sm_count() / tiles);
-  // accuracy: the TMEM accumulator is fp32 with truncating adds, so cap the length of one accumulation
-  // chain at 2048 rows and let the fp32 split-K reduction (round-to-nearest) combine the chunks
-  S = std::max(S, ceil_div(R, 2048));
-  S = std::max(1, std::min(S, ceil_div(R, 128)));
+  const int sms = sm_count();
+  const double per_split = 2.0 * ncat * (double)K * 4.0 / 3.0e12 / 0.77e-6;
+  const int s_lo = std::max(1, ceil_div(R, 2560)), s_hi = std::max(s_lo, std::min(ceil_div(R, 128), 96));
+  int S = s_lo;
+  double best = 1e30;
+  for (int c = s_lo; c <= s_hi; ++c) {
+    const int kc = ceil_div(ceil_div(R, c), 32) * 32;
+    const int sp = ceil_div(R, kc);                      // splits that actually hold rows
+    const double cost = (double)ceil_div(tiles * sp, sms) * (kc / 32) + per_split * sp;
+    if (cost < best) { best = cost; S = c; }
+  }
   b.kchunk = ceil_div(ceil_div(R, S), 32) * 32;
   b.S = ceil_div(R, b.kchunk);
   b.rows_per = 16;                       // rows per staging block: enough blocks to saturate HBM

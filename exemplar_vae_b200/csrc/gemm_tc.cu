@@ -39,7 +39,6 @@ namespace {
 
 constexpr int TBM = 128;        // rows per CTA tile (UMMA M)
 constexpr int TBK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int TSTAGES = 3;
 constexpr int NCONV = 8;        // converter warps
 constexpr int NEPI = 4;         // epilogue warps (one per TMEM lane quadrant)
 constexpr int EPI_WARP0 = 2 + NCONV;
@@ -67,7 +66,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// branch-free (expf is; an IEEE division is not: its slow-path call per element serialises the epilogue's 32
+// independent columns): reciprocal to ~1 ulp, exact 0 for x < -88
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
 
 // The tensor core reads a tf32 operand by DROPPING the 13 low mantissa bits of the 32-bit container (measured on
 // B200: a lo part taken relative to round-to-nearest gives 6e-4 errors, relative to truncation 5e-6), so the raw fp32
@@ -103,13 +104,27 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
 // j overlap the main loop of tile j+1.  Operands arrive as plain fp32 (TMA, swizzled boxes) in the "hi" slot of a
 // stage; the converter warps rewrite the slot in place with the tf32 hi part and store the lo part at the same
 // (swizzled) offset of the "lo" slot, so each SM ingests 4 bytes per operand element instead of two pre-split planes.
-template <int BN, bool A_MN, bool B_MN, int EPI>
+//
+// A_TM: the A operand goes through TENSOR MEMORY instead of shared memory.  The converter thread that owns TMEM lane m
+// reads row m of the raw A tile (16 k-values: the two warps of a lane quadrant split the 32-wide k-block), and writes
+// the hi part (the raw bits) and the lo part with tcgen05.st into the stage's 64 TMEM columns; the MMAs take A from
+// TMEM.  The A tile is then read from shared memory ONCE per k-block (instead of once by the converter + once per MMA,
+// 3 x) and its lo part never touches shared memory: 128 KB instead of 192 KB of shared-memory traffic per k-block,
+// which is what bounds this kernel (measured: TMA-only 0.33, + conversion 0.59, + MMAs 0.91 us per k-block, additive).
+// The stage shrinks to 48 KB, so the ring gets a 4th stage.  An MN-major A tile needs no swizzle here (no MMA reads
+// it): one {128 m, 32 k} box, column m read by lane m without bank conflicts.
+template <int BN, bool A_MN, bool B_MN, int EPI, bool A_TM>
 __global__ void __launch_bounds__(TTHREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  constexpr int TSTAGES = A_TM ? 4 : 3;
   constexpr int A_BYTES = TBM * TBK * 4;   // 16 KB per plane
   constexpr int B_BYTES = BN * TBK * 4;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;
+  constexpr int B_OFF = A_TM ? A_BYTES : 2 * A_BYTES;    // B hi slot inside a stage
   constexpr int RAW_BYTES = A_BYTES + B_BYTES;           // what TMA delivers per stage
+  constexpr uint32_t TM_COLS = A_TM ? 512 : 2 * BN;      // 2 accumulators (+ 4 stages x (32 hi + 32 lo) A columns)
+  constexpr uint32_t TM_A0 = 2 * BN;
+  static_assert(!A_TM || 2 * BN + 4 * 64 <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
   unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -139,7 +154,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,10 +171,12 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], RAW_BYTES);
           unsigned char* sa = smem + s * STAGE_BYTES;
-          unsigned char* sb = sa + 2 * A_BYTES;
+          unsigned char* sb = sa + B_OFF;
           const int k0 = c.kbeg + kb * TBK;
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[s], k0, c.m0);                        // box {32 k, 128 rows}
+          } else if (A_TM) {
+            tma_load_2d(sa, &tmA, &full[s], c.m0, k0);                        // box {128 m, 32 k}, no swizzle
           } else {
 #pragma unroll
             for (int q = 0; q < TBM / 32; ++q)                                // box {32 m, 32 k}
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(TBM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = umma_idesc(TBM, BN, A_TM ? false : A_MN, B_MN);   // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
       unsigned long long w_conv = 0, w_acc = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
@@ -202,8 +219,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           if (tr) w_conv += gtimer() - t0;
           const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sa_lo = sa_hi + A_BYTES;
-          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+          const uint32_t sb_hi = sa_hi + B_OFF;
           const uint32_t sb_lo = sb_hi + B_BYTES;
+          const uint32_t ta_hi = tmem_base + TM_A0 + (uint32_t)(s * 64);
 #pragma unroll
           for (int ks = 0; ks < TBK / 8; ++ks) {
             // K-major : advance 8 tf32 = 32 bytes inside the swizzled 128-byte row; LBO unused, SBO = 8 rows (1024 B)
@@ -211,15 +229,23 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             //           4 k-rows (512 B) of the 32-byte-atom swizzle
             const uint32_t aoff = A_MN ? ks * 1024 : ks * 32;
             const uint32_t boff = B_MN ? ks * 1024 : ks * 32;
-            const uint64_t a_hi = umma_desc(sa_hi + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
-            const uint64_t a_lo = umma_desc(sa_lo + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
             const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             if (p.dbg & 1) continue;
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
-            if (p.dbg & 4) continue;
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+            if (A_TM) {
+              umma_tf32_ts(d_tmem, ta_hi + 32 + 8 * ks, b_hi, idesc, first);           // small terms first
+              if (p.dbg & 4) continue;
+              umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_lo, idesc, 1u);
+              umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, 1u);
+            } else {
+              const uint64_t a_hi = umma_desc(sa_hi + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+              const uint64_t a_lo = umma_desc(sa_lo + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, first);                               // small terms first
+              if (p.dbg & 4) continue;
+              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
@@ -234,6 +260,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     constexpr int CT = 32 * NCONV;
     constexpr int A_IT = A_BYTES / 16 / CT, B_IT = B_BYTES / 16 / CT;
     static_assert(A_BYTES % (16 * CT) == 0 && B_BYTES % (16 * CT) == 0, "tile chunks must divide over the converters");
+    const int qd = warp & 3, kh = (warp - 2) >> 2;         // A_TM: TMEM lane quadrant, half of the k-block
+    const int am = 32 * qd + lane;                         // A_TM: tile row (TMEM lane) of this thread
     int it = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
       const TileCoord c = tile_coord<BN, EPI>(p, t);
@@ -241,21 +269,47 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + s * STAGE_BYTES;
-        unsigned char* sb = sa + 2 * A_BYTES;
+        unsigned char* sb = sa + B_OFF;
         if (p.dbg & 2) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&conv[s]);
           continue;
         }
-        float4 va[A_IT], vb[B_IT];
-#pragma unroll
-        for (int i = 0; i < A_IT; ++i) va[i] = *reinterpret_cast<const float4*>(sa + (ct + CT * i) * 16);
+        float4 vb[B_IT];
 #pragma unroll
         for (int i = 0; i < B_IT; ++i) vb[i] = *reinterpret_cast<const float4*>(sb + (ct + CT * i) * 16);
+        if (A_TM) {
+          uint32_t hi[16], lo[16];
+          if (!A_MN) {
+            // SWIZZLE_128B: 16-byte chunk j of row m sits at chunk position j ^ (m & 7) of the row's 128 bytes
+            const unsigned char* rowp = sa + am * 128;
 #pragma unroll
-        for (int i = 0; i < A_IT; ++i)
-          *reinterpret_cast<float4*>(sa + A_BYTES + (ct + CT * i) * 16) =
-              make_float4(split_lo(va[i].x), split_lo(va[i].y), split_lo(va[i].z), split_lo(va[i].w));
+            for (int i = 0; i < 4; ++i) {
+              const float4 v = *reinterpret_cast<const float4*>(rowp + (((4 * kh + i) ^ (am & 7)) << 4));
+              hi[4 * i] = __float_as_uint(v.x); hi[4 * i + 1] = __float_as_uint(v.y);
+              hi[4 * i + 2] = __float_as_uint(v.z); hi[4 * i + 3] = __float_as_uint(v.w);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)
+              hi[kk] = *reinterpret_cast<const uint32_t*>(sa + (16 * kh + kk) * (TBM * 4) + am * 4);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) lo[e] = __float_as_uint(split_lo(__uint_as_float(hi[e])));
+          const uint32_t ta = tmem_base + ((uint32_t)(32 * qd) << 16) + TM_A0 + (uint32_t)(s * 64 + 16 * kh);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 32, lo);
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          float4 va[A_IT];
+#pragma unroll
+          for (int i = 0; i < A_IT; ++i) va[i] = *reinterpret_cast<const float4*>(sa + (ct + CT * i) * 16);
+#pragma unroll
+          for (int i = 0; i < A_IT; ++i)
+            *reinterpret_cast<float4*>(sa + A_BYTES + (ct + CT * i) * 16) =
+                make_float4(split_lo(va[i].x), split_lo(va[i].y), split_lo(va[i].z), split_lo(va[i].w));
+        }
 #pragma unroll
         for (int i = 0; i < B_IT; ++i)
           *reinterpret_cast<float4*>(sb + B_BYTES + (ct + CT * i) * 16) =
@@ -405,7 +459,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, TM_COLS);
   }
 }
 
@@ -416,11 +470,11 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
     reinterpret_cast<float4*>(out)[i] = i < n4 ? reinterpret_cast<const float4*>(w0)[i] : reinterpret_cast<const float4*>(w1)[i - n4];
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool A_TM>
 int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, cudaStream_t st) {
-  constexpr int STAGE = 2 * TBM * TBK * 4 + 2 * BN * TBK * 4;
-  constexpr int SMEM = TSTAGES * STAGE + 1024 + 256 + EP_BYTES;
-  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI>;
+  constexpr int STAGE = (A_TM ? 1 : 2) * TBM * TBK * 4 + 2 * BN * TBK * 4;
+  constexpr int SMEM = (A_TM ? 4 : 3) * STAGE + 1024 + 256 + EP_BYTES;
+  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI, A_TM>;
   static bool configured = false;
   if (!configured) {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -468,10 +522,18 @@ int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStrea
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
 
+// A through tensor memory (default) or through shared memory (EXVAE_GEMM_ATMEM=0)
+static bool a_tmem_enabled() {
+  static const bool on = [] { const char* e = getenv("EXVAE_GEMM_ATMEM"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   constexpr int BN = 128;
+  const bool atm = a_tmem_enabled();
   CUtensorMap ma, mb;
-  int rc = make_map2d(&ma, g.a, g.a_rows, g.a_cols, g.a_mn ? 32 : TBM, g.a_mn);
+  int rc = (atm && g.a_mn) ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
+                           : make_map2d(&ma, g.a, g.a_rows, g.a_cols, g.a_mn ? 32 : TBM, g.a_mn);
   if (rc) return rc;
   rc = make_map2d(&mb, g.b, g.b_rows, g.b_cols, g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN), g.b_mn);
   if (rc) return rc;
@@ -482,15 +544,19 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   p.bias0 = g.bias0; p.bias1 = g.bias1; p.out0 = g.out0; p.out1 = g.out1; p.out2 = g.out2; p.ldc = g.ldc;
   p.act = g.act; p.lo = g.lo; p.hi = g.hi;
   p.trace = g_trace;
+  if (g_trace) g_trace += 8 * 160;   // the next traced launch writes the next segment
   static const int dbg_env = [] { const char* e = getenv("EXVAE_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg_env;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.c_vec = (g.ldc % 4 == 0) && al16(g.out0) && (!g.out1 || al16(g.out1)) && (!g.out2 || al16(g.out2)) &&
             (g.epi != TC_SPLITK || ((size_t)g.M * g.ldc) % 4 == 0);
-  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, p, st);
-  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, p, st);
-  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, p, st);
-  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, ma, mb, p, st);
+#define EXVAE_TC_DISPATCH(AMN, BMN, EPI)                                            \
+  return atm ? launch<BN, AMN, BMN, EPI, true>(g, ma, mb, p, st) : launch<BN, AMN, BMN, EPI, false>(g, ma, mb, p, st)
+  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) EXVAE_TC_DISPATCH(false, false, TC_GATED);
+  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) EXVAE_TC_DISPATCH(false, false, TC_BIAS_ACT);
+  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) EXVAE_TC_DISPATCH(false, true, TC_PLAIN);
+  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) EXVAE_TC_DISPATCH(true, true, TC_SPLITK);
+#undef EXVAE_TC_DISPATCH
   return EXVAE_ERR_UNSUPPORTED;
 }
 

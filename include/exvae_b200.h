@@ -153,9 +153,10 @@ EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out,
                      void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream);
 /* 1 = tcgen05 3xTF32 backend active on the current device, 0 = fp32 FMA-pipe backend */
 EXVAE_API int exvae_gemm_backend(void);
-/* Debug / profiling aid (tools/gemm_trace.py): when buf != NULL every CTA of the following tensor-core GEMM
- * launches writes 8 uint64 {globaltimer at start, clock64 at start, globaltimer after setup / at the first MMA / at
- * accumulator complete, clock64 at end, globaltimer at end, SM id} at buf[8*linear_cta_index]; NULL switches tracing off. */
+/* Debug / profiling aid (tools/gemm_trace.py): when buf != NULL every (persistent) CTA of the following
+ * tensor-core GEMM launches writes 8 uint64 at buf[8*(160*launch + blockIdx.x)]: {globaltimer at start, -, tiles
+ * done, ns the MMA warp waited for converted operands, ns the epilogue warp was busy, ns the MMA warp waited for
+ * a free accumulator, globaltimer at end, SM id}; NULL switches tracing off. */
 EXVAE_API int exvae_gemm_set_trace(uint64_t* buf);
 
 /* ---------------------------------------------------------------- convolution support (K4)

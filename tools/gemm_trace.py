@@ -21,9 +21,12 @@ dout = torch.randn(R, O, generator=g).cuda()
 L = lib()
 
 
-def summarize(name, buf, ncta):
-    t = buf[: ncta * 8].cpu().numpy().astype(np.int64).reshape(ncta, 8)
+def summarize(name, buf, launch):
+    t = buf[launch * 8 * 160: (launch + 1) * 8 * 160].cpu().numpy().astype(np.int64).reshape(160, 8)
     t = t[t[:, 0] > 0]
+    if len(t) == 0:
+        print(name, ": no trace")
+        return
     span = (t[:, 6].max() - t[:, 0].min()) / 1e3
     life = (t[:, 6] - t[:, 0]) / 1e3
     print(f"{name}: {len(t)} persistent CTAs, kernel span {span:.1f} us; per CTA (median / max):")
@@ -34,22 +37,39 @@ def summarize(name, buf, ncta):
     print(f"   epilogue warp busy                 {np.median(t[:, 4]) / 1e3:8.2f} {t[:, 4].max() / 1e3:8.2f}")
 
 
-# bring the clocks up
-for _ in range(int(os.environ.get("WARM", "300"))):
+def timed(fn, n=20):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    fn()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(n):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) * 1e3 / n
+
+
+for _ in range(int(os.environ.get("WARM", "100"))):
     out = ops.gated_dense(x, Wh, b, Wg, b)
 torch.cuda.synchronize()
-buf = torch.zeros(8 * 200000, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 * 160 * 8, dtype=torch.int64, device="cuda")
 L.exvae_gemm_set_trace(buf.data_ptr())
 out = ops.gated_dense(x, Wh, b, Wg, b)
+out.backward(dout)
 torch.cuda.synchronize()
 L.exvae_gemm_set_trace(None)
-summarize(f"gated fwd R={R} K={K} O={O}", buf, min(148, ((O + 63) // 64) * ((R + 127) // 128)))
-L.exvae_gemm_set_trace(buf.data_ptr())
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-ev[0].record()
-for _ in range(20):
-    out = ops.gated_dense(x, Wh, b, Wg, b)
-ev[1].record()
-torch.cuda.synchronize()
-L.exvae_gemm_set_trace(None)
-print("fwd entry point (debug mode %s): %.1f us per call" % (os.environ.get("EXVAE_GEMM_DEBUG", "0"), ev[0].elapsed_time(ev[1]) * 50))
+summarize(f"gated fwd R={R} K={K} O={O}", buf, 0)
+summarize("gated bwd dx", buf, 1)
+summarize("gated bwd dW", buf, 2)
+print("debug mode %s" % os.environ.get("EXVAE_GEMM_DEBUG", "0"))
+print("fwd entry point: %.1f us per call" % timed(lambda: ops.gated_dense(x, Wh, b, Wg, b)))
+
+
+def fb():
+    o = ops.gated_dense(x, Wh, b, Wg, b)
+    o.backward(dout)
+
+
+print("fwd+bwd: %.1f us per call" % timed(fb))
+x.requires_grad_(False)
+print("fwd+bwd without dx: %.1f us per call" % timed(fb))
