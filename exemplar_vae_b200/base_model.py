@@ -280,14 +280,16 @@ class BaseModel(nn.Module, ABC):
         rows[:B].copy_(x.reshape(B, P))
         ops.gather_rows(self.resident(dataset), exemplars_indices, out=rows[B:])
         h = self._trunk(rows)
+        h, h_batch = ops.shared_rows(h, B)          # mean head: all rows; log-variance head: batch rows only
         mean_all = self._head(self.q_z_mean, h).reshape(B + n, -1)
-        z_q_logvar = self._head(self.q_z_logvar, h[:B]).reshape(B, -1)
+        z_q_logvar = self._head(self.q_z_logvar, h_batch).reshape(B, -1)
         ex_logvar = self.prior_log_variance.expand(n, self.args.z1_size)
-        exemplar_set = (mean_all[B:], ex_logvar, exemplars_indices)
+        mean_batch, mean_bank = ops.split_rows(mean_all, B)
+        exemplar_set = (mean_bank, ex_logvar, exemplars_indices)
         if self.bank_group is not None:
             from .distributed import ShardedBank
             exemplar_set = ShardedBank(exemplar_set, self.args.number_components)
-        return (mean_all[:B], z_q_logvar), exemplar_set
+        return (mean_batch, z_q_logvar), exemplar_set
 
     def cache_z(self, dataset, prior=True, cuda=True):
         """models/BaseModel.py:223-241 — embed the whole (resident) dataset in chunks of 10 000."""

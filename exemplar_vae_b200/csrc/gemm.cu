@@ -322,60 +322,119 @@ __global__ void __launch_bounds__(256) act_dpre_kernel(const float* __restrict__
 }
 
 // Tensor-core backward staging, ONE pass: pre-activation gradient dcat (the fp32 GEMM operand; the GEMM splits it
-// into tf32 hi/lo parts in shared memory) + per-row-chunk column sums (bias gradients).  Replaces dpre + column-sum
-// (2 kernels, 1 extra round trip through HBM).  Thread t owns columns t, t+256, ...: its sums need no cross-thread reduction.
+// into tf32 hi/lo parts in shared memory) + per-block column sums (bias gradients).  Replaces dpre + column-sum
+// (2 kernels, 1 extra round trip through HBM).
 //   MODE 0: gated   dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*out*(1-sig), out = h*sig   (ncat = 2*O)
 //   MODE 1: linear  dcat[r, j] = dout * act'(out)                                      (ncat = O)
+// Thread mapping: RL = max(1, 256 / O) row lanes x O columns (narrow layers such as the 40-wide latent heads keep all
+// 256 threads busy); for O > 256 one lane whose threads own columns t, t+256, ...  A block covers RL*iters rows; the
+// RL lanes' sums are combined through shared memory, so cs_part holds one row per block.
 template <int MODE>
 __global__ void __launch_bounds__(256) dpre_colsum_kernel(const float* __restrict__ dout,
-                                                                const float* __restrict__ h,
-                                                                const float* __restrict__ sig_or_out, int R, int O,
-                                                                int act, float lo, float hi, int rows_per,
-                                                                float* __restrict__ dsplit,
-                                                                float* __restrict__ cs_part) {
+                                                          const float* __restrict__ h,
+                                                          const float* __restrict__ sig_or_out, int R, int O,
+                                                          int act, float lo, float hi, int RL, int iters,
+                                                          float* __restrict__ dsplit,
+                                                          float* __restrict__ cs_part) {
   constexpr int MAXJ = 4;                        // O <= 1024
+  extern __shared__ float sh_cs[];               // RL > 1: [RL][ncat]
   const int ncat = MODE == 0 ? 2 * O : O;
-  const int r0 = blockIdx.x * rows_per, r1 = min(R, r0 + rows_per);
+  const int lanei = RL > 1 ? threadIdx.x / O : 0;
+  const int col0 = RL > 1 ? threadIdx.x - lanei * O : threadIdx.x;
+  const bool active = lanei < RL;
+  const int rbase = blockIdx.x * RL * iters;
   float a0[MAXJ], a1[MAXJ];
 #pragma unroll
   for (int q = 0; q < MAXJ; ++q) a0[q] = a1[q] = 0.f;
-  auto put = [&](size_t idx, float x) { dsplit[idx] = x; };
+  if (active) {
 #pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
+    for (int i = 0; i < iters; ++i) {
+      const int r = rbase + i * RL + lanei;
+      if (r >= R) break;
 #pragma unroll
-    for (int q = 0; q < MAXJ; ++q) {
-      const int j = threadIdx.x + 256 * q;
-      if (j < O) {
-        const size_t e = (size_t)r * O + j;
-        const float d = dout[e];
-        if (MODE == 0) {
-          const float s = sig_or_out[e], ov = h[e];   // ov = layer output h*s
-          const float dh = d * s, dg = d * ov * (1.f - s);
-          put((size_t)r * ncat + j, dh);
-          put((size_t)r * ncat + O + j, dg);
-          a0[q] += dh;
-          a1[q] += dg;
-        } else {
-          float g = d;
-          if (act != EXVAE_ACT_NONE) {
-            const float o = sig_or_out[e];
-            if (act == EXVAE_ACT_SIGMOID) g *= o * (1.f - o);
-            else if (act == EXVAE_ACT_HARDTANH) g = (o > lo && o < hi) ? g : 0.f;
-            else if (act == EXVAE_ACT_RELU) g = o > 0.f ? g : 0.f;
+      for (int q = 0; q < MAXJ; ++q) {
+        const int j = col0 + 256 * q;
+        if (j < O && (q == 0 || RL == 1)) {
+          const size_t e = (size_t)r * O + j;
+          const float d = dout[e];
+          if (MODE == 0) {
+            const float s = sig_or_out[e], ov = h[e];   // ov = layer output h*s
+            const float dh = d * s, dg = d * ov * (1.f - s);
+            dsplit[(size_t)r * ncat + j] = dh;
+            dsplit[(size_t)r * ncat + O + j] = dg;
+            a0[q] += dh;
+            a1[q] += dg;
+          } else {
+            float g = d;
+            if (act != EXVAE_ACT_NONE) {
+              const float o = sig_or_out[e];
+              if (act == EXVAE_ACT_SIGMOID) g *= o * (1.f - o);
+              else if (act == EXVAE_ACT_HARDTANH) g = (o > lo && o < hi) ? g : 0.f;
+              else if (act == EXVAE_ACT_RELU) g = o > 0.f ? g : 0.f;
+            }
+            dsplit[(size_t)r * ncat + j] = g;
+            a0[q] += g;
           }
-          put((size_t)r * ncat + j, g);
-          a0[q] += g;
         }
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < MAXJ; ++q) {
-    const int j = threadIdx.x + 256 * q;
-    if (j < O) {
-      cs_part[(size_t)blockIdx.x * ncat + j] = a0[q];
-      if (MODE == 0) cs_part[(size_t)blockIdx.x * ncat + O + j] = a1[q];
+  if (RL > 1) {
+    if (active) {
+      sh_cs[lanei * ncat + col0] = a0[0];
+      if (MODE == 0) sh_cs[lanei * ncat + O + col0] = a1[0];
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncat; c += 256) {
+      float t = 0.f;
+      for (int l = 0; l < RL; ++l) t += sh_cs[l * ncat + c];
+      cs_part[(size_t)blockIdx.x * ncat + c] = t;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < MAXJ; ++q) {
+      const int j = threadIdx.x + 256 * q;
+      if (j < O) {
+        cs_part[(size_t)blockIdx.x * ncat + j] = a0[q];
+        if (MODE == 0) cs_part[(size_t)blockIdx.x * ncat + O + j] = a1[q];
+      }
+    }
+  }
+}
+
+// ONE launch that finishes a layer's parameter gradients: blocks [0, nred) sum the split-K partials of dW
+// (part [S][M][N] -> out0 rows < mseg, out1 the rest), the following ceil(ncols/32) blocks reduce the staging
+// kernel's column sums cs [S2][ncols] into the bias gradients (32 columns x 8 row lanes per block).
+__global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict__ part, int S, int M, int N, int mseg,
+                                                        float* __restrict__ out0, float* __restrict__ out1, int nred,
+                                                        const float* __restrict__ cs, int S2, int ncols,
+                                                        float* __restrict__ db0, float* __restrict__ db1,
+                                                        int accumulate) {
+  if ((int)blockIdx.x < nred) {
+    const size_t total = (size_t)M * N;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)nred * blockDim.x) {
+      float a = 0.f;
+      for (int s = 0; s < S; ++s) a += part[(size_t)s * total + e];
+      const int m = (int)(e / N);
+      float* dst = m < mseg ? out0 + e : out1 + (e - (size_t)mseg * N);
+      *dst = accumulate ? *dst + a : a;
+    }
+    return;
+  }
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = ((int)blockIdx.x - nred) * 32 + cx;
+  float a = 0.f;
+  if (col < ncols)
+    for (int r = ry; r < S2; r += 8) a += cs[(size_t)r * ncols + col];
+  sh[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && col < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][cx];
+    float* dst = col < mseg ? (db0 ? db0 + col : nullptr) : (db1 ? db1 + (col - mseg) : nullptr);
+    if (dst) *dst = accumulate ? *dst + t : t;
   }
 }
 
@@ -474,9 +533,12 @@ inline bool tc_ok(int R, int K, int OC, const void* x) {
   return tc_enabled() && tc_dims_ok(K) && tc_dims_ok(OC) && OC <= 2048 && al16(x) && R > 0;
 }
 struct TcBwdPlan {
-  int S, kchunk, S2, rows_per, S3, rows_per3;
-  size_t off_dcat, off_dsplit, off_w, off_part, off_cs, off_cs3, bytes;
+  int S, kchunk, S2, RL, iters;
+  size_t off_dcat, off_dsplit, off_w, off_part, off_cs, bytes;
 };
+// upper bound of the staging kernel's block count over all geometries (RL*iters >= 1 row per block, and at most
+// ~592 blocks unless 16 rows per block are not enough)
+inline int stage_blocks_max(int R) { return std::max(ceil_div(R, 16), std::min(R, 600)); }
 inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   TcBwdPlan b;
   // Split the reduction over the R rows so that the persistent kernel's tiles fill whole waves of SMs: cost (in
@@ -497,20 +559,22 @@ inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
   }
   b.kchunk = ceil_div(ceil_div(R, S), 32) * 32;
   b.S = ceil_div(R, b.kchunk);
-  b.rows_per = 16;                       // rows per staging block: enough blocks to saturate HBM
-  b.S2 = ceil_div(R, b.rows_per);
-  b.S3 = std::min(8, b.S2);              // second-level column-sum partials
-  b.rows_per3 = ceil_div(b.S2, b.S3);
+  b.S2 = 0; b.RL = 1; b.iters = 1;       // staging kernel geometry: filled by tc_stage_geometry (depends on the layer's O)
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   b.off_dcat = 0;
   b.off_dsplit = take(sizeof(float) * (size_t)R * ncat);
   b.off_w = take(sizeof(float) * (size_t)ncat * K);
   b.off_part = take(sizeof(float) * (size_t)b.S * ncat * K);
-  b.off_cs = take(sizeof(float) * (size_t)b.S2 * ncat);
-  b.off_cs3 = take(sizeof(float) * (size_t)b.S3 * ncat);
+  b.off_cs = take(sizeof(float) * (size_t)stage_blocks_max(R) * ncat);
   b.bytes = off;
   return b;
+}
+// geometry of dpre_colsum_kernel for a layer with O pre-activation columns per segment
+inline void tc_stage_geometry(TcBwdPlan& b, int R, int O) {
+  b.RL = O >= 256 ? 1 : std::max(1, 256 / O);
+  b.iters = std::min(16, std::max(1, ceil_div(R, 592 * b.RL)));
+  b.S2 = ceil_div(R, b.RL * b.iters);
 }
 
 // dx / dW / db on the tensor cores.  The pre-activation gradient arrives already staged by dpre_colsum_kernel:
@@ -544,17 +608,12 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K,
     g.splits = plan.S; g.kchunk = plan.kchunk;
     rc = tc_gemm_launch(g, st);
     if (rc) return rc;
-    splitk_reduce_kernel<<<ew_blocks((long long)ncat * K), 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0,
-                                                                         dW1 ? dW1 : dW0, accumulate);
-    EXVAE_CUDA(cudaGetLastError());
-  }
-  if (db0 || db1) {   // reduce the staging blocks' column sums: [S2, ncat] -> [S3, ncat] -> bias gradients
-    float* cs = reinterpret_cast<float*>(ws + plan.off_cs);
-    float* cs3 = reinterpret_cast<float*>(ws + plan.off_cs3);
-    dim3 g1(ceil_div(ncat, 32), plan.S3);
-    colsum_partial_kernel<<<g1, 256, 0, st>>>(cs, plan.S2, ncat, plan.rows_per3, cs3);
-    EXVAE_CUDA(cudaGetLastError());
-    colsum_final_kernel<<<ceil_div(ncat, 256), 256, 0, st>>>(cs3, plan.S3, ncat, oseg, db0, db1, accumulate);
+    // split-K reduction of dW and the bias gradients (column sums of the staging blocks) in one launch
+    const int nred = ew_blocks((long long)ncat * K);
+    const int ncs = (db0 || db1) ? ceil_div(ncat, 32) : 0;
+    dw_finish_kernel<<<nred + ncs, 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0, dW1 ? dW1 : dW0, nred,
+                                                 reinterpret_cast<const float*>(ws + plan.off_cs), plan.S2, ncat, db0,
+                                                 db1, accumulate);
     EXVAE_CUDA(cudaGetLastError());
   }
   return EXVAE_OK;
@@ -610,9 +669,11 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
   char* w = static_cast<char*>(ws);
   const bool tc = tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws);
   if (tc) {
-    const TcBwdPlan plan = tc_bwd_plan(R, K, 2 * O);
+    TcBwdPlan plan = tc_bwd_plan(R, K, 2 * O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
-    dpre_colsum_kernel<0><<<plan.S2, 256, 0, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, plan.rows_per,
+    tc_stage_geometry(plan, R, O);
+    const size_t sh = plan.RL > 1 ? sizeof(float) * plan.RL * 2 * O : 0;
+    dpre_colsum_kernel<0><<<plan.S2, 256, sh, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, plan.RL, plan.iters,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
                                                          reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());
@@ -667,9 +728,11 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
   char* w = static_cast<char*>(ws);
   const bool tc = tc_ok(R, K, O, x) && O <= 1024 && al16(W) && al16(ws) && al16(dout);
   if (tc) {
-    const TcBwdPlan plan = tc_bwd_plan(R, K, O);
+    TcBwdPlan plan = tc_bwd_plan(R, K, O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
-    dpre_colsum_kernel<1><<<plan.S2, 256, 0, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.rows_per,
+    tc_stage_geometry(plan, R, O);
+    const size_t sh = plan.RL > 1 ? sizeof(float) * plan.RL * O : 0;
+    dpre_colsum_kernel<1><<<plan.S2, 256, sh, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.RL, plan.iters,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
                                                          reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());

@@ -682,33 +682,25 @@ __global__ void __launch_bounds__(256) prior_bwd_rows_kernel(const float* __rest
   if (tid == 0) rs[b] = rtot;
 }
 
-// dlogvar[d] = -0.5 * ( sum_b rs[b] + sum_b rowdot[b,d] + sum_tile coldot_part[tile,d] )
-__global__ void __launch_bounds__(1024) prior_bwd_dlogvar_kernel(const float* __restrict__ rs,
-                                                                 const float* __restrict__ rowdot,
-                                                                 const float* __restrict__ coldot_part, int B,
-                                                                 int ntile, int D, int LD,
-                                                                 float* __restrict__ dlogvar) {
-  __shared__ float sh[32];
-  __shared__ float s_rs;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// dlogvar[d] = -0.5 * ( sum_b rs[b] + sum_b rowdot[b,d] + sum_tile coldot_part[tile,d] ): one block per dimension
+__global__ void __launch_bounds__(256) prior_bwd_dlogvar_kernel(const float* __restrict__ rs,
+                                                                const float* __restrict__ rowdot,
+                                                                const float* __restrict__ coldot_part, int B,
+                                                                int ntile, int D, int LD,
+                                                                float* __restrict__ dlogvar) {
+  __shared__ float sh[8];
+  const int d = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float a = 0.f;
-  for (int b = tid; b < B; b += blockDim.x) a += rs[b];
+  for (int b = tid; b < B; b += 256) a += rs[b] + rowdot[(size_t)b * LD + d];
+  for (int t = tid; t < ntile; t += 256) a += coldot_part[(size_t)t * LD + d];
   a = warp_sum(a);
   if (lane == 0) sh[warp] = a;
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
-    s_rs = t;
-  }
-  __syncthreads();
-  // one warp per dimension (strided), lanes over rows/tiles
-  for (int d = warp; d < D; d += (blockDim.x >> 5)) {
-    float acc = 0.f;
-    for (int b = lane; b < B; b += 32) acc += rowdot[(size_t)b * LD + d];
-    for (int t = lane; t < ntile; t += 32) acc += coldot_part[(size_t)t * LD + d];
-    acc = warp_sum(acc);
-    if (lane == 0) dlogvar[d] = -0.5f * (s_rs + acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    dlogvar[d] = -0.5f * t;
   }
 }
 
@@ -825,6 +817,6 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
   prior_bwd_rows_kernel<<<B, 256, (8 * w.LD + 8) * sizeof(float), st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, w.ntile, B, D, w.LD,
                                                         w.Bpad, dz, w.rowdot, w.rs);
   EXVAE_CUDA(cudaGetLastError());
-  prior_bwd_dlogvar_kernel<<<1, 1024, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, w.ntile, D, w.LD, dlogvar);
+  prior_bwd_dlogvar_kernel<<<D, 256, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, w.ntile, D, w.LD, dlogvar);
   EXVAE_RETURN_LAST_ERROR();
 }

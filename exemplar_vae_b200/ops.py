@@ -267,6 +267,68 @@ def scatter_rows_(dst, idx, src) -> torch.Tensor:
 
 
 # ======================================================================================
+# row-block views whose backward does not zero-fill and add full-size tensors
+# ======================================================================================
+class _SplitRows(torch.autograd.Function):
+    """(t[:B], t[B:]); the backward writes both gradients into ONE buffer (autograd's slice backward would
+    zero-fill two full-size tensors and add them)."""
+
+    @staticmethod
+    def forward(ctx, t, B):
+        ctx.B = B
+        ctx.shape = t.shape
+        return t[:B], t[B:]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        B = ctx.B
+        if g0 is None and g1 is None:
+            return None, None
+        ref = g0 if g0 is not None else g1
+        out = torch.empty(ctx.shape, dtype=ref.dtype, device=ref.device)
+        if g0 is not None:
+            out[:B].copy_(g0)
+        else:
+            out[:B].zero_()
+        if g1 is not None:
+            out[B:].copy_(g1)
+        else:
+            out[B:].zero_()
+        return out, None
+
+
+def split_rows(t: torch.Tensor, B: int):
+    return _SplitRows.apply(t, B)
+
+
+class _SharedRows(torch.autograd.Function):
+    """(t, t[:B]) for a tensor consumed once in full and once by its first B rows: the backward adds the small
+    gradient into the first rows of the full one in place (that buffer was produced for this node alone by the
+    dense layer's backward) instead of materialising a zero-padded copy."""
+
+    @staticmethod
+    def forward(ctx, t, B):
+        ctx.B = B
+        return t.view_as(t), t[:B]
+
+    @staticmethod
+    def backward(ctx, g_full, g_head):
+        if g_full is None:
+            if g_head is None:
+                return None, None
+            raise ExvaeError("shared_rows: the full-size consumer produced no gradient")
+        if g_head is not None:
+            if not g_full.is_contiguous():
+                g_full = g_full.contiguous()
+            g_full[:ctx.B].add_(g_head)
+        return g_full, None
+
+
+def shared_rows(t: torch.Tensor, B: int):
+    return _SharedRows.apply(t, B)
+
+
+# ======================================================================================
 # K3: dense layers
 # ======================================================================================
 class _GatedDense(torch.autograd.Function):
@@ -311,7 +373,7 @@ class _GatedDense(torch.autograd.Function):
                                         _p(dbh), _p(dWg), _p(dbg), _p(fws), fws.numel() if fws is not None else 0,
                                         _p(ws), ws.numel(), 1 if sink is not None else 0, _stream()),
                 "gated_dense_bwd")
-        _count(5 + (1 if dx is not None else 0))
+        _count(3 + (1 if dx is not None else 0))
         if sink is not None:
             return dx, None, None, None, None, None
         return dx, dWh, dbh, dWg, dbg, None
@@ -388,7 +450,7 @@ class _Linear(torch.autograd.Function):
         L.check(L.exvae_linear_bwd(_p(x), _p(W), _p(out), _p(dout), R, K, O, act, lo, hi, _p(dx), _p(dW), _p(db),
                                    _p(fws), fws.numel() if fws is not None else 0, _p(ws), ws.numel(),
                                    1 if sink is not None else 0, _stream()), "linear_bwd")
-        _count(5 + (1 if dx is not None else 0))
+        _count(3 + (1 if dx is not None else 0))
         if sink is not None:
             return dx, None, None, None, None, None, None
         return dx, dW, db, None, None, None, None
