@@ -326,79 +326,88 @@ __global__ void __launch_bounds__(256) act_dpre_kernel(const float* __restrict__
 // (2 kernels, 1 extra round trip through HBM).
 //   MODE 0: gated   dcat[r, j] = dout*sig ; dcat[r, O+j] = dout*out*(1-sig), out = h*sig   (ncat = 2*O)
 //   MODE 1: linear  dcat[r, j] = dout * act'(out)                                      (ncat = O)
-// Thread mapping: RL = max(1, 256 / O) row lanes x O columns (narrow layers such as the 40-wide latent heads keep all
-// 256 threads busy); for O > 256 one lane whose threads own columns t, t+256, ...  A block covers RL*iters rows; the
-// RL lanes' sums are combined through shared memory, so cs_part holds one row per block.
-template <int MODE>
+// Thread mapping: a thread owns ONE group of VW columns (VW = 4: 16-byte accesses when O % 4 == 0, else VW = 1) and one
+// of RL = 256 / (O/VW) row lanes, so narrow layers (the 40-wide latent heads) and the 300-wide trunk both keep most of
+// the 256 threads busy.  A block covers RL*iters rows; the RL lanes' column sums are combined through shared memory,
+// so cs_part holds one row per block.  Requires O / VW <= 256.
+template <int VW>
+struct VecT { typedef float4 type; };
+template <>
+struct VecT<1> { typedef float type; };
+template <int VW>
+__device__ __forceinline__ void vload(const float* p, float (&v)[VW]) {
+  const typename VecT<VW>::type t = *reinterpret_cast<const typename VecT<VW>::type*>(p);
+  memcpy(v, &t, sizeof(t));
+}
+template <int VW>
+__device__ __forceinline__ void vstore(float* p, const float (&v)[VW]) {
+  typename VecT<VW>::type t;
+  memcpy(&t, v, sizeof(t));
+  *reinterpret_cast<typename VecT<VW>::type*>(p) = t;
+}
+template <int MODE, int VW>
 __global__ void __launch_bounds__(256) dpre_colsum_kernel(const float* __restrict__ dout,
                                                           const float* __restrict__ h,
                                                           const float* __restrict__ sig_or_out, int R, int O,
                                                           int act, float lo, float hi, int RL, int iters,
                                                           float* __restrict__ dsplit,
                                                           float* __restrict__ cs_part) {
-  constexpr int MAXJ = 4;                        // O <= 1024
-  extern __shared__ float sh_cs[];               // RL > 1: [RL][ncat]
+  extern __shared__ float sh_cs[];               // [RL][ncat]
   const int ncat = MODE == 0 ? 2 * O : O;
-  const int lanei = RL > 1 ? threadIdx.x / O : 0;
-  const int col0 = RL > 1 ? threadIdx.x - lanei * O : threadIdx.x;
-  const bool active = lanei < RL;
+  const int Ov = O / VW;
   const int rbase = blockIdx.x * RL * iters;
-  float a0[MAXJ], a1[MAXJ];
+  const int cv = threadIdx.x % Ov, lanei = threadIdx.x / Ov;
+  if (lanei < RL) {
+    float a0[VW], a1[VW];
 #pragma unroll
-  for (int q = 0; q < MAXJ; ++q) a0[q] = a1[q] = 0.f;
-  if (active) {
+    for (int k = 0; k < VW; ++k) a0[k] = a1[k] = 0.f;
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
       const int r = rbase + i * RL + lanei;
       if (r >= R) break;
+      const size_t e = (size_t)r * O + VW * cv;
+      float d[VW];
+      vload<VW>(dout + e, d);
+      if (MODE == 0) {
+        float sg[VW], ov[VW], dh[VW], dg[VW];
+        vload<VW>(sig_or_out + e, sg);
+        vload<VW>(h + e, ov);                    // layer output h*s
 #pragma unroll
-      for (int q = 0; q < MAXJ; ++q) {
-        const int j = col0 + 256 * q;
-        if (j < O && (q == 0 || RL == 1)) {
-          const size_t e = (size_t)r * O + j;
-          const float d = dout[e];
-          if (MODE == 0) {
-            const float s = sig_or_out[e], ov = h[e];   // ov = layer output h*s
-            const float dh = d * s, dg = d * ov * (1.f - s);
-            dsplit[(size_t)r * ncat + j] = dh;
-            dsplit[(size_t)r * ncat + O + j] = dg;
-            a0[q] += dh;
-            a1[q] += dg;
-          } else {
-            float g = d;
-            if (act != EXVAE_ACT_NONE) {
-              const float o = sig_or_out[e];
-              if (act == EXVAE_ACT_SIGMOID) g *= o * (1.f - o);
-              else if (act == EXVAE_ACT_HARDTANH) g = (o > lo && o < hi) ? g : 0.f;
-              else if (act == EXVAE_ACT_RELU) g = o > 0.f ? g : 0.f;
-            }
-            dsplit[(size_t)r * ncat + j] = g;
-            a0[q] += g;
+        for (int k = 0; k < VW; ++k) {
+          dh[k] = d[k] * sg[k];
+          dg[k] = d[k] * ov[k] * (1.f - sg[k]);
+          a0[k] += dh[k];
+          a1[k] += dg[k];
+        }
+        vstore<VW>(dsplit + (size_t)r * ncat + VW * cv, dh);
+        vstore<VW>(dsplit + (size_t)r * ncat + O + VW * cv, dg);
+      } else {
+        if (act != EXVAE_ACT_NONE) {
+          float o[VW];
+          vload<VW>(sig_or_out + e, o);
+#pragma unroll
+          for (int k = 0; k < VW; ++k) {
+            if (act == EXVAE_ACT_SIGMOID) d[k] *= o[k] * (1.f - o[k]);
+            else if (act == EXVAE_ACT_HARDTANH) d[k] = (o[k] > lo && o[k] < hi) ? d[k] : 0.f;
+            else if (act == EXVAE_ACT_RELU) d[k] = o[k] > 0.f ? d[k] : 0.f;
           }
         }
+        vstore<VW>(dsplit + (size_t)r * ncat + VW * cv, d);
+#pragma unroll
+        for (int k = 0; k < VW; ++k) a0[k] += d[k];
       }
+    }
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      sh_cs[lanei * ncat + VW * cv + k] = a0[k];
+      if (MODE == 0) sh_cs[lanei * ncat + O + VW * cv + k] = a1[k];
     }
   }
-  if (RL > 1) {
-    if (active) {
-      sh_cs[lanei * ncat + col0] = a0[0];
-      if (MODE == 0) sh_cs[lanei * ncat + O + col0] = a1[0];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < ncat; c += 256) {
-      float t = 0.f;
-      for (int l = 0; l < RL; ++l) t += sh_cs[l * ncat + c];
-      cs_part[(size_t)blockIdx.x * ncat + c] = t;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < MAXJ; ++q) {
-      const int j = threadIdx.x + 256 * q;
-      if (j < O) {
-        cs_part[(size_t)blockIdx.x * ncat + j] = a0[q];
-        if (MODE == 0) cs_part[(size_t)blockIdx.x * ncat + O + j] = a1[q];
-      }
-    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ncat; c += 256) {
+    float t = 0.f;
+    for (int l = 0; l < RL; ++l) t += sh_cs[l * ncat + c];
+    cs_part[(size_t)blockIdx.x * ncat + c] = t;
   }
 }
 
@@ -572,9 +581,32 @@ inline TcBwdPlan tc_bwd_plan(int R, int K, int ncat) {
 }
 // geometry of dpre_colsum_kernel for a layer with O pre-activation columns per segment
 inline void tc_stage_geometry(TcBwdPlan& b, int R, int O) {
-  b.RL = O >= 256 ? 1 : std::max(1, 256 / O);
+  b.RL = std::max(1, 256 / (O % 4 == 0 ? O / 4 : O));
   b.iters = std::min(16, std::max(1, ceil_div(R, 592 * b.RL)));
   b.S2 = ceil_div(R, b.RL * b.iters);
+}
+
+// one non-blocking side stream + fork/join events per device, created on first use (i.e. in an eager warm-up step,
+// before any graph capture)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+inline SideStream* side_stream() {
+  static SideStream table[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = table[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      (void)cudaGetLastError();
+      s.stream = nullptr;
+      return nullptr;          // fall back to the serial order
+    }
+  }
+  return &s;
 }
 
 // dx / dW / db on the tensor cores.  The pre-activation gradient arrives already staged by dpre_colsum_kernel:
@@ -591,7 +623,17 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K,
     if (rc) return rc;
     wsp = w_own;
   }
-  if (dx) {  // dx[R,K] = dcat[R,ncat] . Wcat[ncat,K]  : A K-major, B MN-major (planes [ncat rows][K cols])
+  // Small layers (the decoder and the batch-only heads: a few tiles each) leave most SMs idle, and dx and dW only share
+  // their inputs: fork dW + the parameter-gradient finish onto a side stream and join afterwards (plain event
+  // fork/join, so a capturing stream turns it into two parallel graph branches).
+  SideStream* side = (dx && R <= 4096) ? side_stream() : nullptr;
+  cudaStream_t sw = st;
+  if (side) {
+    EXVAE_CUDA(cudaEventRecord(side->fork, st));
+    EXVAE_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    sw = side->stream;
+  }
+  if (dx) {  // dx[R,K] = dcat[R,ncat] . Wcat[ncat,K]  : A K-major, B MN-major ([ncat rows][K cols])
     TcGemm g{};
     g.a = dsplit; g.a_rows = R; g.a_cols = ncat; g.a_mn = false;
     g.b = wsp; g.b_rows = ncat; g.b_cols = K; g.b_mn = true;
@@ -606,15 +648,19 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K,
     g.b = x; g.b_rows = R; g.b_cols = K; g.b_mn = true;
     g.M = ncat; g.N = K; g.K = R; g.epi = TC_SPLITK; g.out0 = part; g.ldc = K;
     g.splits = plan.S; g.kchunk = plan.kchunk;
-    rc = tc_gemm_launch(g, st);
+    rc = tc_gemm_launch(g, sw);
     if (rc) return rc;
     // split-K reduction of dW and the bias gradients (column sums of the staging blocks) in one launch
     const int nred = ew_blocks((long long)ncat * K);
     const int ncs = (db0 || db1) ? ceil_div(ncat, 32) : 0;
-    dw_finish_kernel<<<nred + ncs, 256, 0, st>>>(part, plan.S, ncat, K, oseg, dW0, dW1 ? dW1 : dW0, nred,
+    dw_finish_kernel<<<nred + ncs, 256, 0, sw>>>(part, plan.S, ncat, K, oseg, dW0, dW1 ? dW1 : dW0, nred,
                                                  reinterpret_cast<const float*>(ws + plan.off_cs), plan.S2, ncat, db0,
                                                  db1, accumulate);
     EXVAE_CUDA(cudaGetLastError());
+  }
+  if (side) {
+    EXVAE_CUDA(cudaEventRecord(side->join, side->stream));
+    EXVAE_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   }
   return EXVAE_OK;
 }
@@ -667,13 +713,15 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
   EXVAE_CHECK_ARG(x && Wh && Wg && out && sig && dout && dWh && dWg && ws && R > 0 && K > 0 && O > 0);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
-  const bool tc = tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws);
+  const bool tc = tc_ok(R, K, 2 * O, x) && (O % 4 == 0 || O <= 256) && al16(Wh) && al16(Wg) && al16(ws) &&
+                  al16(dout) && al16(out) && al16(sig);
   if (tc) {
     TcBwdPlan plan = tc_bwd_plan(R, K, 2 * O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
     tc_stage_geometry(plan, R, O);
-    const size_t sh = plan.RL > 1 ? sizeof(float) * plan.RL * 2 * O : 0;
-    dpre_colsum_kernel<0><<<plan.S2, 256, sh, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, plan.RL, plan.iters,
+    const size_t sh = sizeof(float) * plan.RL * 2 * O;
+    auto stage_kern = (O % 4 == 0) ? dpre_colsum_kernel<0, 4> : dpre_colsum_kernel<0, 1>;
+    stage_kern<<<plan.S2, 256, sh, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, plan.RL, plan.iters,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
                                                          reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());
@@ -726,13 +774,14 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
   EXVAE_CHECK_ARG(act == EXVAE_ACT_NONE || out != nullptr);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(ws);
-  const bool tc = tc_ok(R, K, O, x) && O <= 1024 && al16(W) && al16(ws) && al16(dout);
+  const bool tc = tc_ok(R, K, O, x) && O <= 1024 && al16(W) && al16(ws) && al16(dout) && (act == EXVAE_ACT_NONE || al16(out));
   if (tc) {
     TcBwdPlan plan = tc_bwd_plan(R, K, O);
     if (ws_bytes < plan.bytes) return EXVAE_ERR_WORKSPACE;
     tc_stage_geometry(plan, R, O);
-    const size_t sh = plan.RL > 1 ? sizeof(float) * plan.RL * O : 0;
-    dpre_colsum_kernel<1><<<plan.S2, 256, sh, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.RL, plan.iters,
+    const size_t sh = sizeof(float) * plan.RL * O;
+    auto stage_kern = (O % 4 == 0) ? dpre_colsum_kernel<1, 4> : dpre_colsum_kernel<1, 1>;
+    stage_kern<<<plan.S2, 256, sh, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.RL, plan.iters,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
                                                          reinterpret_cast<float*>(w + plan.off_cs));
     EXVAE_CUDA(cudaGetLastError());
