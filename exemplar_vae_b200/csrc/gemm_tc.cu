@@ -1,23 +1,25 @@
 // K3 on the 5th-generation tensor cores: error-compensated 3xTF32 GEMM (sm_100a, tcgen05 + TMEM + TMA).
 //
 // The 1e-4 ELBO parity bar rules out single-pass TF32/BF16 operands, so every fp32
-// operand element is split into hi = tf32(x) and lo = tf32(x - hi) (both exactly representable, so
-// the tensor core's own operand truncation is irrelevant) and each k-step issues three MMAs into
-// the same TMEM accumulator:  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (the lo*lo term is 2^-22).
-// The split happens IN the kernel, on the tile in shared memory: the operands stay plain fp32 in HBM
-// and every SM ingests 4 bytes per element (pre-split planes cost 8 and an extra HBM pass).
+// operand element x is used as hi + lo with hi = x truncated to tf32 (what the tensor core does to the raw
+// bits anyway, measured) and lo = tf32(x - hi), and each k-step issues three MMAs into the same TMEM
+// accumulator:  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   (the dropped lo*lo term is ~2^-21).
+// The split happens IN the kernel: the operands stay plain fp32 in HBM and every SM ingests 4 bytes per
+// element (pre-split planes cost 8 and an extra HBM pass).
 //
 // Kernel anatomy (persistent: one CTA per SM walks 128 x BN output tiles; 448 threads):
-//   warp 0       TMA producer: per 32-wide k-block, bulk-tensor loads of the fp32 A and B tiles
-//                (SWIZZLE_128B boxes) into the hi slots of a 3-stage shared-memory ring that runs
-//                continuously across tiles
-//   warps 2-9    converters: rewrite the hi slot in place, store lo at the same swizzled offset of the
-//                lo slot, fence.proxy.async, arrive on the stage's "converted" barrier
-//   warp 1       allocates 2 x BN TMEM columns (two accumulators); one elected lane issues
-//                tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 4 k-steps x 3 products per stage;
-//                tcgen05.commit frees the stage / publishes the finished accumulator
+//   warp 0       TMA producer: per 32-wide k-block, bulk-tensor loads of the fp32 A and B tiles into a
+//                4-stage shared-memory ring that runs continuously across tiles
+//   warps 2-9    converters: B: store lo at the same swizzled offset of the stage's lo slot (the raw
+//                tile is the hi operand); A: thread = tile row, raw bits + lo -> tensor memory
+//                (tcgen05.st); fences, then arrive on the stage's "converted" barrier
+//   warp 1       allocates the 512 TMEM columns (two accumulators + 4 x 64 A columns); one elected lane
+//                issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; A from TMEM, B from shared memory)
+//                x 4 k-steps x 3 products per stage; tcgen05.commit frees the stage / publishes the
+//                finished accumulator
 //   warps 10-13  epilogue of tile j while the MMA warp works on tile j+1: tcgen05.ld (32 lanes x 32
-//                columns) -> bias / activation / gate -> global stores; warp%4 = TMEM lane quadrant
+//                columns) -> bias / activation / gate -> shared-memory transposition patch -> 128-byte
+//                row-segment stores; warp%4 = TMEM lane quadrant
 // Both operand majors are supported straight from row-major global memory, so the three GEMMs of a
 // dense layer need no transposed copies:
 //   forward  x[R,K] W[O,K]^T              A K-major,  B K-major
@@ -39,6 +41,7 @@ namespace {
 
 constexpr int TBM = 128;        // rows per CTA tile (UMMA M)
 constexpr int TBK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TSTAGES = 4;
 constexpr int NCONV = 8;        // converter warps
 constexpr int NEPI = 4;         // epilogue warps (one per TMEM lane quadrant)
 constexpr int EPI_WARP0 = 2 + NCONV;
@@ -101,30 +104,28 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
 
 // Persistent: one CTA per SM walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the shared-memory ring and
 // its barriers run continuously across tiles (no pipeline drain), and two TMEM accumulators let the epilogue of tile
-// j overlap the main loop of tile j+1.  Operands arrive as plain fp32 (TMA, swizzled boxes) in the "hi" slot of a
-// stage; the converter warps rewrite the slot in place with the tf32 hi part and store the lo part at the same
-// (swizzled) offset of the "lo" slot, so each SM ingests 4 bytes per operand element instead of two pre-split planes.
+// j overlap the main loop of tile j+1.  Operands arrive as plain fp32 (TMA); the raw B tile is the hi operand and the
+// converter warps store its lo part at the same (swizzled) offset of the stage's "lo" slot.
 //
-// A_TM: the A operand goes through TENSOR MEMORY instead of shared memory.  The converter thread that owns TMEM lane m
-// reads row m of the raw A tile (16 k-values: the two warps of a lane quadrant split the 32-wide k-block), and writes
-// the hi part (the raw bits) and the lo part with tcgen05.st into the stage's 64 TMEM columns; the MMAs take A from
-// TMEM.  The A tile is then read from shared memory ONCE per k-block (instead of once by the converter + once per MMA,
-// 3 x) and its lo part never touches shared memory: 128 KB instead of 192 KB of shared-memory traffic per k-block,
-// which is what bounds this kernel (measured: TMA-only 0.33, + conversion 0.59, + MMAs 0.91 us per k-block, additive).
-// The stage shrinks to 48 KB, so the ring gets a 4th stage.  An MN-major A tile needs no swizzle here (no MMA reads
-// it): one {128 m, 32 k} box, column m read by lane m without bank conflicts.
-template <int BN, bool A_MN, bool B_MN, int EPI, bool A_TM>
+// The A operand goes through TENSOR MEMORY instead of shared memory.  The converter thread that owns TMEM lane m reads
+// row m of the raw A tile (16 k-values: the two warps of a lane quadrant split the 32-wide k-block) and writes the hi
+// part (the raw bits) and the lo part with tcgen05.st into the stage's 64 TMEM columns; the MMAs take A from TMEM.
+// The A tile is then read from shared memory ONCE per k-block (instead of once by the converter + once per MMA, 3 x)
+// and its lo part never touches shared memory: 128 KB instead of 192 KB of shared-memory traffic per k-block, which
+// is what bounds this kernel (measured: TMA-only 0.33, + conversion 0.59, + MMAs 0.91 us per k-block, additive;
+// profiles/r1_gemm_persistent.md).  A stage is 48 KB, so the ring has 4 of them.  An MN-major A tile needs no
+// swizzle (no MMA reads it): one {128 m, 32 k} box, column m read by lane m without bank conflicts.
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(TTHREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  constexpr int TSTAGES = A_TM ? 4 : 3;
-  constexpr int A_BYTES = TBM * TBK * 4;   // 16 KB per plane
-  constexpr int B_BYTES = BN * TBK * 4;
-  constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;
-  constexpr int B_OFF = A_TM ? A_BYTES : 2 * A_BYTES;    // B hi slot inside a stage
+  constexpr int A_BYTES = TBM * TBK * 4;   // 16 KB: raw A tile
+  constexpr int B_BYTES = BN * TBK * 4;    // raw (= hi) B tile; the lo tile follows it
+  constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  constexpr int B_OFF = A_BYTES;                         // B hi slot inside a stage
   constexpr int RAW_BYTES = A_BYTES + B_BYTES;           // what TMA delivers per stage
-  constexpr uint32_t TM_COLS = A_TM ? 512 : 2 * BN;      // 2 accumulators (+ 4 stages x (32 hi + 32 lo) A columns)
+  constexpr uint32_t TM_COLS = 512;                      // 2 accumulators + TSTAGES x (32 hi + 32 lo) A columns
   constexpr uint32_t TM_A0 = 2 * BN;
-  static_assert(!A_TM || 2 * BN + 4 * 64 <= 512, "TMEM budget");
+  static_assert(2 * BN + TSTAGES * 64 <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
   unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -175,12 +176,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           const int k0 = c.kbeg + kb * TBK;
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[s], k0, c.m0);                        // box {32 k, 128 rows}
-          } else if (A_TM) {
-            tma_load_2d(sa, &tmA, &full[s], c.m0, k0);                        // box {128 m, 32 k}, no swizzle
           } else {
-#pragma unroll
-            for (int q = 0; q < TBM / 32; ++q)                                // box {32 m, 32 k}
-              tma_load_2d(sa + q * 4096, &tmA, &full[s], c.m0 + 32 * q, k0);
+            tma_load_2d(sa, &tmA, &full[s], c.m0, k0);                        // box {128 m, 32 k}, no swizzle
           }
           if (!B_MN) {
             if (EPI == TC_GATED) {                                             // box {32 k, BN/2 rows}: h rows, g rows
@@ -200,7 +197,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(TBM, BN, A_TM ? false : A_MN, B_MN);   // A in TMEM is [m lanes][k columns]
+      constexpr uint32_t idesc = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
       unsigned long long w_conv = 0, w_acc = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
@@ -217,35 +214,23 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           mbar_wait(&conv[s], ph);
           tc_fence_after();
           if (tr) w_conv += gtimer() - t0;
-          const uint32_t sa_hi = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sa_lo = sa_hi + A_BYTES;
-          const uint32_t sb_hi = sa_hi + B_OFF;
+          const uint32_t sb_hi = smem_u32(smem + s * STAGE_BYTES) + B_OFF;
           const uint32_t sb_lo = sb_hi + B_BYTES;
           const uint32_t ta_hi = tmem_base + TM_A0 + (uint32_t)(s * 64);
 #pragma unroll
           for (int ks = 0; ks < TBK / 8; ++ks) {
-            // K-major : advance 8 tf32 = 32 bytes inside the swizzled 128-byte row; LBO unused, SBO = 8 rows (1024 B)
-            // MN-major: advance 8 k-rows = 1024 bytes; LBO = next 32-wide MN chunk (4096 B), SBO = next group of
-            //           4 k-rows (512 B) of the 32-byte-atom swizzle
-            const uint32_t aoff = A_MN ? ks * 1024 : ks * 32;
+            // B K-major : advance 8 tf32 = 32 bytes inside the swizzled 128-byte row; LBO unused, SBO = 8 rows (1024 B)
+            // B MN-major: advance 8 k-rows = 1024 bytes; LBO = next 32-wide MN chunk (4096 B), SBO = next group of
+            //             4 k-rows (512 B) of the 32-byte-atom swizzle
             const uint32_t boff = B_MN ? ks * 1024 : ks * 32;
             const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             if (p.dbg & 1) continue;
             const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
-            if (A_TM) {
-              umma_tf32_ts(d_tmem, ta_hi + 32 + 8 * ks, b_hi, idesc, first);           // small terms first
-              if (p.dbg & 4) continue;
-              umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_lo, idesc, 1u);
-              umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, 1u);
-            } else {
-              const uint64_t a_hi = umma_desc(sa_hi + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
-              const uint64_t a_lo = umma_desc(sa_lo + aoff, A_MN ? 4096 : 16, A_MN ? 512 : 1024, A_MN ? 1 : 2);
-              umma_tf32(d_tmem, a_lo, b_hi, idesc, first);                               // small terms first
-              if (p.dbg & 4) continue;
-              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-            }
+            umma_tf32_ts(d_tmem, ta_hi + 32 + 8 * ks, b_hi, idesc, first);           // A_lo x B_hi: small terms first
+            if (p.dbg & 4) continue;
+            umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_lo, idesc, 1u);                   // A_hi x B_lo
+            umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, 1u);                   // A_hi x B_hi
           }
           umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
@@ -258,10 +243,11 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     // ---------------------------------------------------------------- converters (warps 2..9)
     const int ct = tid - 64;                               // 0 .. 32*NCONV-1
     constexpr int CT = 32 * NCONV;
-    constexpr int A_IT = A_BYTES / 16 / CT, B_IT = B_BYTES / 16 / CT;
-    static_assert(A_BYTES % (16 * CT) == 0 && B_BYTES % (16 * CT) == 0, "tile chunks must divide over the converters");
-    const int qd = warp & 3, kh = (warp - 2) >> 2;         // A_TM: TMEM lane quadrant, half of the k-block
-    const int am = 32 * qd + lane;                         // A_TM: tile row (TMEM lane) of this thread
+    constexpr int B_IT = B_BYTES / 16 / CT;
+    static_assert(B_BYTES % (16 * CT) == 0, "B tile chunks must divide over the converters");
+    static_assert(NCONV == 8, "two converter warps per TMEM lane quadrant split the k-block");
+    const int qd = warp & 3, kh = (warp - 2) >> 2;         // TMEM lane quadrant, half of the k-block
+    const int am = 32 * qd + lane;                         // tile row (= TMEM lane) of this thread
     int it = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
       const TileCoord c = tile_coord<BN, EPI>(p, t);
@@ -278,7 +264,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         float4 vb[B_IT];
 #pragma unroll
         for (int i = 0; i < B_IT; ++i) vb[i] = *reinterpret_cast<const float4*>(sb + (ct + CT * i) * 16);
-        if (A_TM) {
+        {
           uint32_t hi[16], lo[16];
           if (!A_MN) {
             // SWIZZLE_128B: 16-byte chunk j of row m sits at chunk position j ^ (m & 7) of the row's 128 bytes
@@ -301,14 +287,6 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           tmem_st16(ta + 32, lo);
           tmem_st_wait();
           tc_fence_before();
-        } else {
-          float4 va[A_IT];
-#pragma unroll
-          for (int i = 0; i < A_IT; ++i) va[i] = *reinterpret_cast<const float4*>(sa + (ct + CT * i) * 16);
-#pragma unroll
-          for (int i = 0; i < A_IT; ++i)
-            *reinterpret_cast<float4*>(sa + A_BYTES + (ct + CT * i) * 16) =
-                make_float4(split_lo(va[i].x), split_lo(va[i].y), split_lo(va[i].z), split_lo(va[i].w));
         }
 #pragma unroll
         for (int i = 0; i < B_IT; ++i)
@@ -470,11 +448,11 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
     reinterpret_cast<float4*>(out)[i] = i < n4 ? reinterpret_cast<const float4*>(w0)[i] : reinterpret_cast<const float4*>(w1)[i - n4];
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool A_TM>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, cudaStream_t st) {
-  constexpr int STAGE = (A_TM ? 1 : 2) * TBM * TBK * 4 + 2 * BN * TBK * 4;
-  constexpr int SMEM = (A_TM ? 4 : 3) * STAGE + 1024 + 256 + EP_BYTES;
-  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI, A_TM>;
+  constexpr int STAGE = TBM * TBK * 4 + 2 * BN * TBK * 4;
+  constexpr int SMEM = TSTAGES * STAGE + 1024 + 256 + EP_BYTES;
+  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -522,18 +500,12 @@ int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStrea
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
 
-// A through tensor memory (default) or through shared memory (EXVAE_GEMM_ATMEM=0)
-static bool a_tmem_enabled() {
-  static const bool on = [] { const char* e = getenv("EXVAE_GEMM_ATMEM"); return !(e && atoi(e) == 0); }();
-  return on;
-}
-
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   constexpr int BN = 128;
-  const bool atm = a_tmem_enabled();
   CUtensorMap ma, mb;
-  int rc = (atm && g.a_mn) ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
-                           : make_map2d(&ma, g.a, g.a_rows, g.a_cols, g.a_mn ? 32 : TBM, g.a_mn);
+  // A never feeds an MMA from shared memory: an MN-major tile is one un-swizzled {128 m, 32 k} box
+  int rc = g.a_mn ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
+                  : make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, false);
   if (rc) return rc;
   rc = make_map2d(&mb, g.b, g.b_rows, g.b_cols, g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN), g.b_mn);
   if (rc) return rc;
@@ -550,13 +522,10 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.c_vec = (g.ldc % 4 == 0) && al16(g.out0) && (!g.out1 || al16(g.out1)) && (!g.out2 || al16(g.out2)) &&
             (g.epi != TC_SPLITK || ((size_t)g.M * g.ldc) % 4 == 0);
-#define EXVAE_TC_DISPATCH(AMN, BMN, EPI)                                            \
-  return atm ? launch<BN, AMN, BMN, EPI, true>(g, ma, mb, p, st) : launch<BN, AMN, BMN, EPI, false>(g, ma, mb, p, st)
-  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) EXVAE_TC_DISPATCH(false, false, TC_GATED);
-  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) EXVAE_TC_DISPATCH(false, false, TC_BIAS_ACT);
-  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) EXVAE_TC_DISPATCH(false, true, TC_PLAIN);
-  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) EXVAE_TC_DISPATCH(true, true, TC_SPLITK);
-#undef EXVAE_TC_DISPATCH
+  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, p, st);
+  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, p, st);
+  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, p, st);
+  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, ma, mb, p, st);
   return EXVAE_ERR_UNSUPPORTED;
 }
 
