@@ -18,6 +18,9 @@
 // D = 40 is not an MMA-friendly K and the 1e-4 parity bar excludes tf32/bf16 operands
 // (SURVEY.md §7), so the contraction runs on the fp32 FMA pipe with an 8x4 register tile per
 // thread; the tensor-core variant only pays for D >= 64 and is a later-round item.
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -54,6 +57,13 @@ struct PriorWs {
   float* coldot_part;  // [ntile, LD]
   float* rowdot;       // [Bpad, LD]
   float* rs;           // [Bpad]
+  // tensor-core backward (prior_bwd_tc.cu)
+  int NG;              // D rounded up to 16 (UMMA N of the W.ms / W^T.zs contractions); 0 = path not applicable
+  float* zsT;          // [2, NG, Bpad]
+  float* msT;          // [2, NG, Cpad]
+  float* glp;          // [Bpad]
+  float* lsp;          // [Bpad]
+  int64_t* zip;        // [Bpad]
   size_t bytes;
 };
 
@@ -100,8 +110,21 @@ inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
     w.coldot_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.LD);
     w.rowdot = (float*)take(sizeof(float) * (size_t)w.Bpad * w.LD);
     w.rs = (float*)take(sizeof(float) * w.Bpad);
+    w.NG = (w.KP && D <= 64) ? ceil_div(D, 16) * 16 : 0;
+    if (w.NG) {
+      w.zsT = (float*)take(sizeof(float) * 2 * (size_t)w.NG * w.Bpad);
+      w.msT = (float*)take(sizeof(float) * 2 * (size_t)w.NG * w.Cpad);
+      w.glp = (float*)take(sizeof(float) * w.Bpad);
+      w.lsp = (float*)take(sizeof(float) * w.Bpad);
+      w.zip = (int64_t*)take(sizeof(int64_t) * w.Bpad);
+    }
   } else {
     w.dzs_part = w.rowsum_part = w.coldot_part = w.rowdot = w.rs = nullptr;
+  }
+  if (!need_bwd || !w.NG) {
+    w.NG = 0;
+    w.zsT = w.msT = w.glp = w.lsp = nullptr;
+    w.zip = nullptr;
   }
   w.bytes = off;
   return w;
@@ -704,6 +727,11 @@ __global__ void __launch_bounds__(256) prior_bwd_dlogvar_kernel(const float* __r
   }
 }
 
+inline bool bwd_simt_forced() {
+  static const bool forced = [] { const char* e = getenv("EXVAE_PRIOR_BWD"); return e && strcmp(e, "simt") == 0; }();
+  return forced;
+}
+
 int stage(const PriorWs& w, const float* z, const float* mu, const float* logvar, const int64_t* mu_idx, int B, int C,
           int D, cudaStream_t st) {
   const int rows = w.Cpad + w.Bpad;
@@ -800,6 +828,26 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
     if (rc) return rc;
   }
   const bool mask = z_idx && mu_idx;
+  if (w.NG && prior_tc_enabled() && !bwd_simt_forced()) {
+    // tensor-core path: transposed operand planes + padded row arrays, two passes of prior_bwd_tc_kernel, then the
+    // same row / dlogvar reductions as the FMA path (over nsplit partials instead of one per 64-column tile)
+    int rc = prior_bwd_prep_launch(w.zs, w.ms, grad_log_p, lse2, mask ? z_idx : nullptr, B, C, D, w.LD, w.Bpad, w.Cpad,
+                                   w.NG, w.zsT, w.msT, w.glp, w.lsp, w.zip, st);
+    if (rc) return rc;
+    PriorBwdTcArgs a{};
+    a.zp = w.zp; a.mp = w.mp; a.zsT = w.zsT; a.msT = w.msT; a.zs = w.zs; a.ms = w.ms; a.glp = w.glp; a.lsp = w.lsp;
+    a.zip = mask ? w.zip : nullptr; a.cidx = w.cidx; a.isig = w.isig;
+    a.Bpad = w.Bpad; a.Cpad = w.Cpad; a.KP = w.KP; a.NG = w.NG; a.LD = w.LD; a.B = B; a.C = C; a.D = D;
+    a.dzs_part = w.dzs_part; a.rowsum_part = w.rowsum_part; a.dmu = dmu; a.coldot_part = w.coldot_part;
+    int nsplit = 0, ntile = 0;
+    rc = prior_bwd_tc_launch(a, &nsplit, &ntile, st);
+    if (rc) return rc;
+    prior_bwd_rows_kernel<<<B, 256, (8 * w.LD + 8) * sizeof(float), st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, nsplit, B,
+                                                                         D, w.LD, w.Bpad, dz, w.rowdot, w.rs);
+    EXVAE_CUDA(cudaGetLastError());
+    prior_bwd_dlogvar_kernel<<<D, 256, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, ntile, D, w.LD, dlogvar);
+    EXVAE_RETURN_LAST_ERROR();
+  }
   const BwdSmem L = bwd_smem_layout(w.LD);
   auto launch = [&](auto kern) -> int {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));

@@ -16,6 +16,33 @@ struct PriorTcArgs {
   float* part;       // [Bpad, nsplit, 4]
 };
 
+// K1 backward on the tensor cores (prior_bwd_tc.cu).  All pointers are workspace arrays staged by
+// prior_stage_kernel / prior_bwd_prep (padded to Bpad / Cpad rows).
+struct PriorBwdTcArgs {
+  const float* zp;   // [2, Bpad, KP]  hi/lo planes of (zs*log2e | 1 | 0..)
+  const float* mp;   // [2, Cpad, KP]  hi/lo planes of (ms | nb2 | 0..)
+  const float* zsT;  // [2, NG, Bpad]  hi/lo planes of zs^T (rows d >= D are zero)
+  const float* msT;  // [2, NG, Cpad]  hi/lo planes of ms^T
+  const float* zs;   // [Bpad, LD]
+  const float* ms;   // [Cpad, LD]
+  const float* glp;  // [Bpad] upstream gradient (0 in the padding)
+  const float* lsp;  // [Bpad] base-2 row log-sum (+inf in the padding)
+  const int64_t* zip;   // [Bpad] dataset index of each z row (INT64_MIN in the padding), NULL => no mask
+  const int64_t* cidx;  // [Cpad] dataset index of each exemplar (INT64_MIN in the padding)
+  const float* isig;    // [LD] 1/sigma
+  int Bpad, Cpad, KP, NG, LD, B, C, D;
+  float* dzs_part;      // [nsplit, Bpad, LD]   (out) per-split W.ms
+  float* rowsum_part;   // [nsplit, Bpad]       (out) per-split row sums of W
+  float* dmu;           // [C, D]               (out)
+  float* coldot_part;   // [Cpad/128, LD]       (out) per column tile sum_n dms[n,d]*ms[n,d]
+};
+// launches both passes; *nsplit_out = number of dzs/rowsum partials per row, *ntile_out = column tiles of coldot_part
+int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out, cudaStream_t st);
+// transposed hi/lo planes + padded per-row arrays for the backward
+int prior_bwd_prep_launch(const float* zs, const float* ms, const float* g, const float* lse2, const int64_t* z_idx,
+                          int B, int C, int D, int LD, int Bpad, int Cpad, int NG, float* zsT, float* msT, float* glp,
+                          float* lsp, int64_t* zip, cudaStream_t st);
+
 bool prior_tc_enabled();
 // launches the kernel; *nsplit_out = number of partials written per row
 int prior_fwd_tc_launch(const PriorTcArgs& a, int* nsplit_out, cudaStream_t st);
