@@ -30,8 +30,8 @@ from .layers import NonLinear, he_init
 
 class DeviceRng:
     """Philox4x32-10 stream (seed, call-site subsequence, device counter).  The counter lives in
-    device memory and is advanced by a kernel after every draw, so a captured CUDA graph draws
-    fresh numbers on every replay."""
+    device memory ([offset, ticket]) and every drawing kernel advances it itself once all its blocks
+    have read it, so a captured CUDA graph draws fresh numbers on every replay."""
 
     SUB_BERNOULLI, SUB_EXEMPLAR, SUB_EPS = 1, 2, 3
 
@@ -41,26 +41,20 @@ class DeviceRng:
 
     def counter(self, device) -> torch.Tensor:
         if self._counter is None or self._counter.device != torch.device(device):
-            self._counter = torch.zeros(1, dtype=torch.int64, device=device)
+            self._counter = torch.zeros(2, dtype=torch.int64, device=device)
         return self._counter
 
     def bernoulli(self, p):
         c = self.counter(p.device)
-        out = ops.rng_bernoulli(p, self.seed, c, self.SUB_BERNOULLI)
-        ops.rng_advance_(c, 1)
-        return out
+        return ops.rng_bernoulli(p, self.seed, c, self.SUB_BERNOULLI, advance=True)
 
     def normal(self, shape, device, sub=0):
         c = self.counter(device)
-        out = ops.rng_normal(tuple(shape), self.seed, c, self.SUB_EPS + sub, device)
-        ops.rng_advance_(c, 1)
-        return out
+        return ops.rng_normal(tuple(shape), self.seed, c, self.SUB_EPS + sub, device, advance=True)
 
     def randint(self, low, high, n, device):
         c = self.counter(device)
-        out = ops.rng_randint(low, high, n, self.seed, c, self.SUB_EXEMPLAR, device)
-        ops.rng_advance_(c, 1)
-        return out
+        return ops.rng_randint(low, high, n, self.seed, c, self.SUB_EXEMPLAR, device, advance=True)
 
 
 def to_nhwc(x, chw):

@@ -229,10 +229,22 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+// Optional in-kernel advance of the draw counter: every block reads counter[0] before it does anything else and takes
+// a ticket (counter[1], wraps back to 0) when it is done; the block that takes the last ticket therefore runs after
+// all reads and bumps the counter, which saves the separate one-thread "advance" launch after each draw.
+__device__ __forceinline__ void rng_finish(uint64_t* counter, int advance) {
+  if (!advance || !counter) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(reinterpret_cast<unsigned int*>(counter + 1), gridDim.x - 1);
+    if (t == gridDim.x - 1) counter[0] += 1;
+  }
+}
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 
 __global__ void __launch_bounds__(256) rng_bernoulli_kernel(const float* __restrict__ p, long long n, uint64_t seed,
-                                                            const uint64_t* __restrict__ counter, uint64_t subseq,
+                                                            uint64_t* counter, uint64_t subseq, int advance,
                                                             float* __restrict__ out) {
   const uint64_t off = counter ? *counter : 0;
   const long long nq = (n + 3) / 4;
@@ -246,9 +258,10 @@ __global__ void __launch_bounds__(256) rng_bernoulli_kernel(const float* __restr
       if (e < n) out[e] = u01(rr[j]) < p[e] ? 1.f : 0.f;
     }
   }
+  rng_finish(counter, advance);
 }
-__global__ void __launch_bounds__(256) rng_normal_kernel(long long n, uint64_t seed, const uint64_t* __restrict__ counter,
-                                                         uint64_t subseq, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) rng_normal_kernel(long long n, uint64_t seed, uint64_t* counter, uint64_t subseq,
+                                                         int advance, float* __restrict__ out) {
   const uint64_t off = counter ? *counter : 0;
   const long long nq = (n + 3) / 4;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
@@ -275,10 +288,11 @@ __global__ void __launch_bounds__(256) rng_normal_kernel(long long n, uint64_t s
       if (e < n) out[e] = v[j];
     }
   }
+  rng_finish(counter, advance);
 }
 __global__ void __launch_bounds__(256) rng_randint_kernel(long long low, unsigned long long range, long long n,
-                                                          uint64_t seed, const uint64_t* __restrict__ counter,
-                                                          uint64_t subseq, int64_t* __restrict__ out) {
+                                                          uint64_t seed, uint64_t* counter, uint64_t subseq,
+                                                          int advance, int64_t* __restrict__ out) {
   const uint64_t off = counter ? *counter : 0;
   const long long nq = (n + 1) / 2;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
@@ -288,6 +302,7 @@ __global__ void __launch_bounds__(256) rng_randint_kernel(long long low, unsigne
     if (q * 2 < n) out[q * 2] = low + (long long)(a % range);
     if (q * 2 + 1 < n) out[q * 2 + 1] = low + (long long)(b % range);
   }
+  rng_finish(counter, advance);
 }
 __global__ void rng_advance_kernel(uint64_t* counter, uint64_t by) { *counter += by; }
 
@@ -447,20 +462,21 @@ extern "C" int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int
   EXVAE_RETURN_LAST_ERROR();
 }
 
-extern "C" int exvae_rng_bernoulli(const float* p, int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq,
-                                   float* out, exvae_stream_t stream) {
+extern "C" int exvae_rng_bernoulli(const float* p, int64_t n, uint64_t seed, uint64_t* counter, uint64_t subseq,
+                                   int advance, float* out, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(p && out && n > 0);
-  EW_LAUNCH(rng_bernoulli_kernel, (n + 3) / 4, p, n, seed, counter, subseq, out);
+  EW_LAUNCH(rng_bernoulli_kernel, (n + 3) / 4, p, n, seed, counter, subseq, advance, out);
 }
-extern "C" int exvae_rng_normal(int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq, float* out,
+extern "C" int exvae_rng_normal(int64_t n, uint64_t seed, uint64_t* counter, uint64_t subseq, int advance, float* out,
                                 exvae_stream_t stream) {
   EXVAE_CHECK_ARG(out && n > 0);
-  EW_LAUNCH(rng_normal_kernel, (n + 3) / 4, n, seed, counter, subseq, out);
+  EW_LAUNCH(rng_normal_kernel, (n + 3) / 4, n, seed, counter, subseq, advance, out);
 }
-extern "C" int exvae_rng_randint(int64_t low, int64_t high, int64_t n, uint64_t seed, const uint64_t* counter,
-                                 uint64_t subseq, int64_t* out, exvae_stream_t stream) {
+extern "C" int exvae_rng_randint(int64_t low, int64_t high, int64_t n, uint64_t seed, uint64_t* counter,
+                                 uint64_t subseq, int advance, int64_t* out, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(out && n > 0 && high > low);
-  EW_LAUNCH(rng_randint_kernel, (n + 1) / 2, low, (unsigned long long)(high - low), n, seed, counter, subseq, out);
+  EW_LAUNCH(rng_randint_kernel, (n + 1) / 2, low, (unsigned long long)(high - low), n, seed, counter, subseq, advance,
+            out);
 }
 extern "C" int exvae_rng_advance(uint64_t* counter, uint64_t by, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(counter != nullptr);

@@ -488,6 +488,11 @@ bool tc_enabled() {
 bool tc_dims_ok(int pitch) { return pitch > 0 && pitch % 4 == 0; }
 
 void tc_set_trace(unsigned long long* buf) { g_trace = buf; }
+unsigned long long* tc_take_trace(size_t words) {
+  unsigned long long* t = g_trace;
+  if (g_trace) g_trace += words;
+  return t;
+}
 
 int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(w0) & 15) || (reinterpret_cast<uintptr_t>(w1) & 15) ||

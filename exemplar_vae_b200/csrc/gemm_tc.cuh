@@ -26,6 +26,7 @@ struct TcGemm {
 bool tc_enabled();                       // sm_100 device, driver entry point found, not disabled by EXVAE_GEMM=simt
 bool tc_dims_ok(int rows_pitch_elems);   // TMA needs 16-byte row pitches
 void tc_set_trace(unsigned long long* buf);   // debug: 8 u64 per CTA of the NEXT launches (null = off)
+unsigned long long* tc_take_trace(size_t words);   // debug: current trace segment (or null), then advance by `words`
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st);
 // out[0..n) = w0, out[n..2n) = w1 (the two weight tensors of a gated layer as one [2*O, K] operand); n % 4 == 0
 int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStream_t st);

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 
+#include "gemm_tc.cuh"
 #include "tc_common.cuh"
 
 namespace exvae {
@@ -48,6 +49,7 @@ struct BwdP {
   const float* zs; const float* ms; const float* isig;
   int Bpad, Cpad, KP, NG, LD, B, C, D, ny, nsplit;
   float* dzs_part; float* rowsum_part; float* dmu; float* coldot_part;
+  unsigned long long* trace;   // debug (exvae_gemm_set_trace): 8 words per CTA, null in production
 };
 
 template <bool TR, bool MASK>
@@ -78,7 +80,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // TR = false: X = block blockIdx.y of 128 latents, Y = bank tiles [y0, y1) of split blockIdx.x
+  unsigned long long* tr = p.trace ? p.trace + 8 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  auto stamp = [&](int i) {
+    if (tr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tr[i] = t;
+    }
+  };
+  if (tid == 0) stamp(0);
+  // TR = false: X = block blockIdx.y of 128 latents, Y = bank tiles [y0, y1) of split blockIdx.x (of nsplit)
   // TR = true : X = bank tile blockIdx.x,            Y = all row blocks
   const int xi = TR ? blockIdx.x : blockIdx.y;
   const int y0 = TR ? 0 : (int)(((long long)p.ny * blockIdx.x) / p.nsplit);
@@ -134,11 +145,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       const uint32_t idesc_s = umma_idesc(128, 128, false, false);
       const uint32_t idesc_g = umma_idesc(128, p.NG, false, false);
       mbar_wait(x_full, 0);
+      stamp(1);
       const uint32_t x0 = smem_u32(sX), k0 = smem_u32(sYK), t0 = smem_u32(sYT);
       for (int y = y0; y < y1; ++y) {
         const int it = y - y0, ph = it & 1;
         mbar_wait(yk_full, ph);
         tc_fence_after();
+        if (it == 0) stamp(2);
         for (int ks = 0; ks < nks; ++ks) {
           const int kb = ks >> 2, kk = ks & 3;
           const uint32_t off_hi = (kb * 2 + 0) * BT_BOX + kk * 32, off_lo = (kb * 2 + 1) * BT_BOX + kk * 32;
@@ -166,6 +179,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
         umma_commit(yt_empty);          // the transposed tile can be refilled (and W may be overwritten: in-order pipe)
       }
       umma_commit(g_full);
+      stamp(3);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..9
@@ -233,6 +247,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     if (y1 > y0) {
       mbar_wait(g_full, 0);
       tc_fence_after();
+      if (tid == 64) stamp(4);
       if (dbase < p.NG) {
         tmem_ld32(lane_addr + TM_G + dbase, gv);
         tmem_ld_wait();
@@ -247,28 +262,46 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       if (half == 0) p.rowsum_part[(size_t)blockIdx.x * p.Bpad + xrow] = tot;
     } else {
       // dmu[n,d] = (G[n,d] - colsum_n ms[n,d]) / sigma_d ;  coldot[d] = sum_n (G[n,d] - colsum_n ms[n,d]) ms[n,d]
-      const float* msr = p.ms + (size_t)xrow * p.LD;
+      // (per-thread work first, all loads up front; the column dots go through a [128][65] shared-memory patch in the
+      //  idle X region instead of 32 warp reductions per thread)
+      float* pdm = reinterpret_cast<float*>(sX);              // X tile is dead: every S MMA has retired
+      const float* msr = p.ms + (size_t)xrow * p.LD + dbase;
+      float mv[32];
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dbase + j4 < p.LD) t = *reinterpret_cast<const float4*>(msr + j4);   // LD % 4 == 0, rows 16-byte aligned
+        mv[j4] = t.x; mv[j4 + 1] = t.y; mv[j4 + 2] = t.z; mv[j4 + 3] = t.w;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int d = dbase + j;
-        float pd = 0.f;
-        if (d < p.D) {                                        // warp-uniform
-          const float mv = msr[d];
-          const float dv = __uint_as_float(gv[j]) - tot * mv;
-          if (xrow < p.C) p.dmu[(size_t)xrow * p.D + d] = dv * p.isig[d];
-          pd = dv * mv;
-          pd = warp_sum(pd);
-          if (lane == 0) cd[q * 64 + d] = pd;
-        }
+        const float dv = d < p.D ? __uint_as_float(gv[j]) - tot * mv[j] : 0.f;
+        if (d < p.D && xrow < p.C) p.dmu[(size_t)xrow * p.D + d] = dv * p.isig[d];
+        pdm[r * 65 + d] = dv * mv[j];
       }
       named_bar_sync(1, BT_EPI_WARPS * 32);
-      const int e = tid - 64;
+      const int e = tid - 64;                                  // 0..255: 4 row groups x 64 columns
+      const int dcol = e & 63, rg = e >> 6;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) acc += pdm[(rg * 32 + rr) * 65 + dcol];
+      cd[rg * 64 + dcol] = acc;
+      named_bar_sync(1, BT_EPI_WARPS * 32);
       if (e < p.LD)
         p.coldot_part[(size_t)xi * p.LD + e] = e < p.D ? (cd[e] + cd[64 + e]) + (cd[128 + e] + cd[192 + e]) : 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) {
+    stamp(5);
+    if (tr) {
+      unsigned int sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      tr[6] = sm;
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -345,11 +378,13 @@ int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out
   };
   // pass 1: lanes = latents, columns = the split's bank tiles      -> dzs / rowsum partials
   p.ny = ntile; p.nsplit = nsplit;
+  p.trace = tc_take_trace(8 * 400);
   rc = a.zip ? launch(prior_bwd_tc_kernel<false, true>, dim3(nsplit, rbs), mz, mm, mmt)
              : launch(prior_bwd_tc_kernel<false, false>, dim3(nsplit, rbs), mz, mm, mmt);
   if (rc) return rc;
   // pass 2: lanes = exemplars of one tile, columns = all row blocks -> dmu, coldot
   p.ny = rbs; p.nsplit = 1;
+  p.trace = tc_take_trace(8 * 400);
   return a.zip ? launch(prior_bwd_tc_kernel<true, true>, dim3(ntile), mm, mz, mzt)
                : launch(prior_bwd_tc_kernel<true, false>, dim3(ntile), mm, mz, mzt);
 }

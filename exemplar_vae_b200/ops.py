@@ -651,29 +651,44 @@ def elbo_reduce(RE, KL, beta: float, average: bool):
 # counter-based RNG
 # ======================================================================================
 @torch.no_grad()
-def rng_bernoulli(p, seed: int, counter: Optional[torch.Tensor], subseq: int) -> torch.Tensor:
+def _adv(counter, advance) -> int:
+    """advance=True lets the drawing kernel bump counter[0] itself (needs the 2-word counter of DeviceRng)."""
+    if not advance:
+        return 0
+    if counter is None or counter.numel() < 2:
+        raise ExvaeError("in-kernel RNG advance needs a [2] int64 counter tensor (offset, ticket)")
+    return 1
+
+
+@torch.no_grad()
+def rng_bernoulli(p, seed: int, counter: Optional[torch.Tensor], subseq: int, advance: bool = False) -> torch.Tensor:
     L = lib()
     p = _f32(p)
     out = torch.empty_like(p)
-    L.check(L.exvae_rng_bernoulli(_p(p), p.numel(), seed, _p(counter), subseq, _p(out), _stream()), "rng_bernoulli")
+    L.check(L.exvae_rng_bernoulli(_p(p), p.numel(), seed, _p(counter), subseq, _adv(counter, advance), _p(out),
+                                  _stream()), "rng_bernoulli")
     _count(1)
     return out
 
 
 @torch.no_grad()
-def rng_normal(shape, seed: int, counter: Optional[torch.Tensor], subseq: int, device) -> torch.Tensor:
+def rng_normal(shape, seed: int, counter: Optional[torch.Tensor], subseq: int, device,
+               advance: bool = False) -> torch.Tensor:
     L = lib()
     out = torch.empty(shape, dtype=torch.float32, device=device)
-    L.check(L.exvae_rng_normal(out.numel(), seed, _p(counter), subseq, _p(out), _stream()), "rng_normal")
+    L.check(L.exvae_rng_normal(out.numel(), seed, _p(counter), subseq, _adv(counter, advance), _p(out), _stream()),
+            "rng_normal")
     _count(1)
     return out
 
 
 @torch.no_grad()
-def rng_randint(low: int, high: int, n: int, seed: int, counter: Optional[torch.Tensor], subseq: int, device):
+def rng_randint(low: int, high: int, n: int, seed: int, counter: Optional[torch.Tensor], subseq: int, device,
+                advance: bool = False):
     L = lib()
     out = torch.empty((n,), dtype=torch.int64, device=device)
-    L.check(L.exvae_rng_randint(low, high, n, seed, _p(counter), subseq, _p(out), _stream()), "rng_randint")
+    L.check(L.exvae_rng_randint(low, high, n, seed, _p(counter), subseq, _adv(counter, advance), _p(out), _stream()),
+            "rng_randint")
     _count(1)
     return out
 
@@ -707,6 +722,9 @@ class _LinComb(torch.autograd.Function):
         for i, c in enumerate(ctx.coeffs):
             if not ctx.needs_input_grad[i + 1]:
                 grads.append(None)
+                continue
+            if c == 1.0:
+                grads.append(g)        # the upstream gradient itself: no kernel
                 continue
             d = torch.empty_like(g)
             L.check(L.exvae_lincomb4(_p(g), None, None, None, c, 0.0, 0.0, 0.0, g.numel(), _p(d), _stream()),

@@ -215,14 +215,16 @@ EXVAE_API int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int 
 /* ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
  * Device-side replacements for torch.bernoulli (utils/training.py:31), torch.randint
  * (models/BaseModel.py:245,257) and normal_() (models/BaseModel.py:81).  `counter` is a device
- * uint64 that the kernel reads as the stream offset, so graph replays draw fresh numbers once
- * exvae_rng_advance has bumped it.                                                            */
-EXVAE_API int exvae_rng_bernoulli(const float* p, int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq, float* out,
-                        exvae_stream_t stream);
-EXVAE_API int exvae_rng_normal(int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq, float* out,
+ * uint64 that the kernel reads as the stream offset, so graph replays draw fresh numbers once it has been
+ * bumped: by exvae_rng_advance, or by the drawing kernel itself when advance != 0 (then `counter` must hold TWO
+ * uint64: counter[0] the offset, counter[1] a zero-initialised ticket word the kernel uses to find its last block,
+ * which adds 1 to counter[0] after every block has read it).  counter may be NULL (offset 0, no advance).   */
+EXVAE_API int exvae_rng_bernoulli(const float* p, int64_t n, uint64_t seed, uint64_t* counter, uint64_t subseq, int advance,
+                        float* out, exvae_stream_t stream);
+EXVAE_API int exvae_rng_normal(int64_t n, uint64_t seed, uint64_t* counter, uint64_t subseq, int advance, float* out,
                      exvae_stream_t stream);
-EXVAE_API int exvae_rng_randint(int64_t low, int64_t high, int64_t n, uint64_t seed, const uint64_t* counter, uint64_t subseq,
-                      int64_t* out, exvae_stream_t stream);
+EXVAE_API int exvae_rng_randint(int64_t low, int64_t high, int64_t n, uint64_t seed, uint64_t* counter, uint64_t subseq,
+                      int advance, int64_t* out, exvae_stream_t stream);
 EXVAE_API int exvae_rng_advance(uint64_t* counter, uint64_t by, exvae_stream_t stream);
 
 /* ---------------------------------------------------------------- AdamNormGrad (utils/optimizer.py:32-80)

@@ -346,6 +346,16 @@ def test_rng_statistics(ops):
     ops.rng_advance_(c, 1)
     e2 = ops.rng_normal((64,), 1234, c, 3, "cuda")
     assert torch.equal(e1, e[:64]) and not torch.equal(e1, e2)
+    # in-kernel advance: the drawing kernel bumps counter[0] itself (ticket word counter[1] returns to 0)
+    c2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+    a0 = ops.rng_normal((n,), 1234, c2, 3, "cuda", advance=True)
+    a1 = ops.rng_normal((64,), 1234, c2, 3, "cuda", advance=True)
+    b1 = ops.rng_bernoulli(p, 1234, c2, 1, advance=True)
+    torch.cuda.synchronize()
+    assert c2.tolist() == [3, 0]
+    assert torch.equal(a0, e) and torch.equal(a1, e2)            # offsets 0 and 1 of the same stream
+    c.fill_(2)
+    assert torch.equal(b1, ops.rng_bernoulli(p, 1234, c, 1))
 
 
 def test_adam_normgrad_vs_oracle():
