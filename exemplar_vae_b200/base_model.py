@@ -25,7 +25,7 @@ import torch.nn as nn
 
 from . import ops
 from .distributions import log_bernoulli, log_logistic_256, log_normal_diag, log_normal_standard, pairwise_distance
-from .layers import NonLinear, he_init
+from .layers import NonLinear, he_init, normal_init
 
 
 class DeviceRng:
@@ -83,7 +83,7 @@ class BaseModel(nn.Module, ABC):
         self._resident_cache = {}
 
         if self.args.prior == 'vampprior':
-            raise NotImplementedError("prior='vampprior' (per-component log-variance bank) is SURVEY §8f-4, not built yet")
+            self.add_pseudoinputs()
         if self.args.prior == 'exemplar_prior':
             self.prior_log_variance = torch.nn.Parameter(torch.randn((1)))
 
@@ -180,6 +180,32 @@ class BaseModel(nn.Module, ABC):
         return ops.prior_logprob_matrix(z, centers, lv, z_indices if masked else None,
                                         center_indices if masked else None)
 
+    # ------------------------------------------------------------------ VampPrior
+    def add_pseudoinputs(self):
+        """models/BaseModel.py:130-139 — C learned pseudo-inputs as the weight of a bias-free layer fed the identity."""
+        C, P = int(self.args.number_components), int(np.prod(self.args.input_size))
+        self.means = NonLinear(C, P, bias=False, activation=nn.Hardtanh(min_val=0.0, max_val=1.0))
+        if getattr(self.args, "use_training_data_init", False):
+            self.means.linear.weight.data = self.args.pseudoinputs_mean
+        else:
+            normal_init(self.means.linear, getattr(self.args, "pseudoinputs_mean", -0.05),
+                        getattr(self.args, "pseudoinputs_std", 0.01))
+        self.register_buffer("idle_input", torch.eye(C, C), persistent=False)
+
+    def pseudo_embedding(self):
+        """(z_p_mean [C,D], z_p_logvar [C,D]) = q_z(means(idle_input), prior=True)  (BaseModel.py:86-88)"""
+        return self.q_z(self.means(self.idle_input), prior=True)
+
+    def log_p_z_vampprior(self, z, exemplars_embedding, sum=True):
+        """models/BaseModel.py:84-96 (+ the log-sum-exp of :123-125 when ``sum``)."""
+        if exemplars_embedding is None:
+            z_p_mean, z_p_logvar = self.pseudo_embedding()
+        else:
+            z_p_mean, z_p_logvar = exemplars_embedding[0], exemplars_embedding[1]
+        if not sum:
+            return ops.vamp_logprob_matrix(z, z_p_mean, z_p_logvar)
+        return ops.vamp_lse(z, z_p_mean, z_p_logvar)
+
     def log_p_z(self, z, exemplars_embedding, sum=True, test=None):
         """models/BaseModel.py:111-128"""
         z, z_indices = z
@@ -187,6 +213,8 @@ class BaseModel(nn.Module, ABC):
             test = not self.training
         if self.args.prior == 'standard':
             return log_normal_standard(z, dim=1)
+        elif self.args.prior == 'vampprior':
+            return self.log_p_z_vampprior(z, exemplars_embedding, sum=sum)
         elif self.args.prior == 'exemplar_prior':
             if not sum:
                 return self.log_p_z_exemplar(z, z_indices, exemplars_embedding, test)
@@ -206,6 +234,10 @@ class BaseModel(nn.Module, ABC):
         dev = self.prior_device()
         if self.args.prior == 'standard':
             return self.rng.normal((N, self.args.z1_size), dev)
+        if self.args.prior == 'vampprior':
+            means = self.means(self.idle_input)[0:N]
+            mean, logvar = self.q_z(means)
+            return self.reparameterize(mean, logvar)
         rand_indices = self.rng.randint(0, self.args.training_set_size, N, dev)
         exemplars = ops.gather_rows(self.resident(dataset), rand_indices)
         mean, logvar = self.q_z(exemplars, prior=True)

@@ -19,7 +19,10 @@ def load_all_pseudo_input(args, model, dataset):
         return (exemplars_z, exemplars_log_var, torch.arange(len(exemplars_z), device=exemplars_z.device))
     if args.prior == 'standard':
         return None
-    raise NotImplementedError("vampprior pseudo-inputs are not built (SURVEY §8f-4)")
+    if args.prior == 'vampprior':      # utils/evaluation.py:60-64: embed the pseudo-inputs once
+        with torch.no_grad():
+            return model.pseudo_embedding()
+    raise Exception('Wrong name of the prior!')
 
 
 @torch.no_grad()

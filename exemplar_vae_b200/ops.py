@@ -14,7 +14,7 @@ import torch
 from ._lib import ACT_HARDTANH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ExvaeError, lib
 
 __all__ = [
-    "prior_lse", "pairwise_distance", "log_normal_diag_vectorized", "prior_logprob_matrix", "knn_topk", "knn_merge",
+    "prior_lse", "vamp_lse", "vamp_logprob_matrix", "pairwise_distance", "log_normal_diag_vectorized", "prior_logprob_matrix", "knn_topk", "knn_merge",
     "unique_positions", "gather_rows", "scatter_rows_", "gated_dense", "linear", "reparameterize",
     "log_normal_diag", "log_normal_standard", "log_bernoulli", "log_logistic_256", "elbo_reduce",
     "rng_bernoulli", "rng_normal", "rng_randint", "launch_count", "reset_launch_count",
@@ -189,6 +189,55 @@ def prior_logprob_matrix(z, mu, logvar, z_idx=None, mu_idx=None) -> torch.Tensor
                                          _p(counts), _stream()), "prior_logprob_matrix")
     _count(2 if (z_idx is not None and mu_idx is not None) else 1)
     return out
+
+
+# ======================================================================================
+# VampPrior (per-component mean and log-variance)
+# ======================================================================================
+@torch.no_grad()
+def vamp_logprob_matrix(z, mean, logvar) -> torch.Tensor:
+    """models/BaseModel.py:84-96 — the [B,C] matrix log N(z_b | mean_c, exp(logvar_c)) - log C."""
+    L = lib()
+    z, mean, logvar = _f32(z, "z"), _f32(mean, "mean"), _f32(logvar, "logvar")
+    B, D = z.shape
+    C = mean.shape[0]
+    out = torch.empty((B, C), dtype=torch.float32, device=z.device)
+    L.check(L.exvae_vamp_logprob_matrix(_p(z), _p(mean), _p(logvar), B, C, D, _p(out), _stream()), "vamp_logprob_matrix")
+    _count(1)
+    return out
+
+
+class _VampLSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, mean, logvar):
+        L = lib()
+        z, mean, logvar = _f32(z, "z"), _f32(mean, "mean"), _f32(logvar, "logvar")
+        B, D = z.shape
+        C = mean.shape[0]
+        mat = torch.empty((B, C), dtype=torch.float32, device=z.device)
+        log_p = torch.empty((B,), dtype=torch.float32, device=z.device)
+        L.check(L.exvae_vamp_lse_fwd(_p(z), _p(mean), _p(logvar), B, C, D, _p(mat), _p(log_p), _stream()), "vamp_lse_fwd")
+        _count(2)
+        ctx.save_for_backward(z, mean, logvar, mat, log_p)
+        return log_p
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        z, mean, logvar, mat, log_p = ctx.saved_tensors
+        g = _f32(g)
+        B, D = z.shape
+        C = mean.shape[0]
+        dz, dmean, dlogvar = torch.empty_like(z), torch.empty_like(mean), torch.empty_like(logvar)
+        L.check(L.exvae_vamp_lse_bwd(_p(z), _p(mean), _p(logvar), _p(mat), _p(log_p), _p(g), B, C, D, _p(dz), _p(dmean),
+                                     _p(dlogvar), _stream()), "vamp_lse_bwd")
+        _count(2)
+        return dz, dmean, dlogvar
+
+
+def vamp_lse(z, mean, logvar) -> torch.Tensor:
+    """log p(z) under the VampPrior: log-sum-exp over the C components (BaseModel.py:111-128, sum=True)."""
+    return _VampLSE.apply(z, mean, logvar)
 
 
 @torch.no_grad()

@@ -96,6 +96,20 @@ EXVAE_API int exvae_prior_logprob_matrix(const float* z, const float* mu, const 
                                const int64_t* mu_idx, int B, int C, int D, float* out, int* row_counts,
                                exvae_stream_t stream);
 
+/* ---------------------------------------------------------------- VampPrior (prior == 'vampprior')
+ * models/BaseModel.py:84-96,111-128: mixture of C Gaussians with per-component mean AND log-variance
+ * (both [C,D], the encodings of the learned pseudo-inputs).  logprob_matrix writes the reference's [B,C]
+ * matrix  sum_d log N(z_b | mean_c, exp(logvar_c)) - log C  (log_p_z(sum=False)); lse_fwd also reduces it with the
+ * max-shifted log-sum-exp and keeps the matrix (`mat`, caller-owned [B,C]) for the backward, which recomputes
+ * the mixture weights from it.                                                                          */
+EXVAE_API int exvae_vamp_logprob_matrix(const float* z, const float* mean, const float* logvar, int B, int C, int D,
+                                        float* out, exvae_stream_t stream);
+EXVAE_API int exvae_vamp_lse_fwd(const float* z, const float* mean, const float* logvar, int B, int C, int D, float* mat,
+                                 float* log_p, exvae_stream_t stream);
+EXVAE_API int exvae_vamp_lse_bwd(const float* z, const float* mean, const float* logvar, const float* mat,
+                                 const float* log_p, const float* grad_log_p, int B, int C, int D, float* dz,
+                                 float* dmean, float* dlogvar, exvae_stream_t stream);
+
 /* ---------------------------------------------------------------- kNN exemplar selection (K2)
  * pairwise_distance(z, bank).topk(k, largest=False) (models/BaseModel.py:263-264): fp64
  * expansion distance rounded to fp32, k smallest per row sorted ascending, ties -> lowest

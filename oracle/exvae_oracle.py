@@ -298,6 +298,8 @@ def vae_loss(p, args, x, x_indices, eps, exemplars, exemplar_indices, beta=1.0, 
         else:
             ex_mean, ex_logvar, ex_idx = exemplars_embedding
         log_p = t_log_p_z_exemplar(z, x_indices, ex_mean, ex_logvar[0], ex_idx, masked)
+    elif args.prior == "vampprior":
+        log_p = t_log_p_z_vampprior(p, args, z, exemplars_embedding)
     else:
         log_p = (-0.5 * z * z - 0.5 * LOG_2PI).sum(1)
     log_q = t_log_normal_diag(z, mean, logvar)
@@ -306,6 +308,26 @@ def vae_loss(p, args, x, x_indices, eps, exemplars, exemplar_indices, beta=1.0, 
     if average:
         return loss.mean(), RE.mean(), KL.mean()
     return loss, RE, KL
+
+
+def t_vamp_logprob_matrix(z, pm, plv):
+    """models/BaseModel.py:90-96: log_normal_diag(z[:,None], mean[None], logvar[None], dim=2) - log C  -> [B,C]"""
+    C = pm.shape[0]
+    t = -0.5 * (plv[None] + LOG_2PI + (z[:, None, :] - pm[None]) ** 2 / torch.exp(plv[None]))
+    return t.sum(2) - math.log(C)
+
+
+def t_log_p_z_vampprior(p, args, z, exemplars_embedding=None):
+    """models/BaseModel.py:84-96 + :123-125 — pseudo-inputs = Hardtanh(0,1)(I @ W^T) (BaseModel.py:130-139), encoded
+    with q_z(prior=True) (both heads: the prior is not the exemplar prior), then max-shifted log-sum-exp."""
+    if exemplars_embedding is None:
+        X = torch.clamp(p["means.linear.weight"].t(), 0.0, 1.0)
+        pm, plv = vae_q_z(p, args, X, prior=True)
+    else:
+        pm, plv = exemplars_embedding[0], exemplars_embedding[1]
+    prob = t_vamp_logprob_matrix(z, pm, plv)
+    pmax = prob.max(1)[0]
+    return pmax + torch.log(torch.exp(prob - pmax[:, None]).sum(1))
 
 
 # ---- model_name == 'hvae_2level' (models/HVAE_2level.py:15-66, models/AbsHModel.py) ---
@@ -393,6 +415,9 @@ def init_params(args, seed=0) -> Dict[str, torch.Tensor]:
     p: Dict[str, torch.Tensor] = {}
     if args.prior == "exemplar_prior":
         p["prior_log_variance"] = torch.randn(1, generator=g)
+    if args.prior == "vampprior":       # BaseModel.py:130-139: N(pseudoinputs_mean, pseudoinputs_std)
+        P = int(np.prod(args.input_size))
+        p["means.linear.weight"] = -0.05 + 0.01 * torch.randn(P, args.number_components, generator=g)
     for name, fin, fout in shapes:
         p[name + ".weight"] = torch.randn(fout, fin, generator=g) * math.sqrt(2.0 / fin)
         bound = 1.0 / math.sqrt(fin)

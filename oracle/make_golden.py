@@ -179,7 +179,8 @@ def golden_model_step(model_name, hidden, seed, side=28, T=128, N=64, B=12, chan
                     input_size=[chans, side, side], z1_size=D, z2_size=D, **extra)
     model = build_ref_model(args, seed)
     with torch.no_grad():
-        model.prior_log_variance.fill_(-1.3)
+        if args.prior == "exemplar_prior":
+            model.prior_log_variance.fill_(-1.3)
     compact = extra.pop("_compact", False) if False else model_name in ("convhvae_2level", "single_conv")
     if compact:     # big models: parameters are regenerated from seeds by the tests (oracle.synth_params)
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -269,6 +270,11 @@ def main():
     np.savez_compressed(os.path.join(OUT, "vae_step.npz"), **golden_model_step("vae", 48, 3))
     np.savez_compressed(os.path.join(OUT, "hvae_step.npz"), **golden_model_step("hvae_2level", 24, 4, side=14))
     np.savez_compressed(os.path.join(OUT, "approx.npz"), **golden_approx())
+    # f4: the same step under the VampPrior (20 pseudo-inputs spread over [0,1] so that Hardtanh(0,1) clips some)
+    np.savez_compressed(os.path.join(OUT, "vamp_step.npz"),
+                        **golden_model_step("vae", 32, 9, side=14, T=64, N=20, B=10, prior="vampprior",
+                                            use_training_data_init=False, pseudoinputs_mean=0.4,
+                                            pseudoinputs_std=0.35))
     np.savez_compressed(os.path.join(OUT, "convhvae_step.npz"),
                         **golden_model_step("convhvae_2level", 300, 6, side=28, T=24, N=6, B=4))
     np.savez_compressed(os.path.join(OUT, "single_conv_step.npz"),

@@ -227,6 +227,28 @@ def test_gather_scatter_rows(ops):
     assert torch.equal(dst, ref)
 
 
+# ------------------------------------------------------------------ VampPrior
+@pytest.mark.parametrize("B,C,D", [(100, 500, 40), (7, 33, 24), (512, 1000, 40)])
+def test_vamp_lse_fwd_bwd_vs_oracle(ops, B, C, D):
+    g = torch.Generator().manual_seed(B + C)
+    z = torch.randn(B, D, generator=g)
+    pm = torch.randn(C, D, generator=g)
+    plv = torch.clamp(torch.randn(C, D, generator=g), -6, 2)
+    gout = torch.randn(B, generator=g)
+    ts = [t.double().requires_grad_(True) for t in (z, pm, plv)]
+    mat = O.t_vamp_logprob_matrix(*ts)
+    ref = torch.logsumexp(mat, 1)
+    ref.backward(gout.double())
+    cs = [t.cuda().requires_grad_(True) for t in (z, pm, plv)]
+    close(ops.vamp_logprob_matrix(*cs), mat.detach(), rtol=1e-5, atol=1e-4)
+    lp = ops.vamp_lse(*cs)
+    close(lp, ref.detach(), rtol=1e-5, atol=1e-4)
+    lp.backward(gout.cuda())
+    for c, t in zip(cs, ts):
+        scale = t.grad.abs().max().item()
+        close(c.grad, t.grad, rtol=1e-4, atol=1e-5 * scale)
+
+
 # ------------------------------------------------------------------ K3
 @pytest.mark.parametrize("R,K,Oo", [(12, 784, 48), (300, 300, 300), (1000, 40, 300), (77, 96, 24), (257, 300, 784),
                                     (5, 7, 3)])

@@ -24,14 +24,14 @@ def build(args, g=None):
     return model
 
 
-def _golden_step(g, model_name, fused=False):
+def _golden_step(g, model_name, fused=False, prior="exemplar_prior"):
     import exemplar_vae_b200 as E
     from exemplar_vae_b200 import ops
     from exemplar_vae_b200.distributed import FlatGrads
     side = int(g["side"])
     N = len(g["ex_idx"])
     args = O.make_args(model_name=model_name, hidden_size=int(g["hidden"]), number_components=N,
-                       training_set_size=int(g["T"]), input_size=[1, side, side], device="cuda")
+                       training_set_size=int(g["T"]), input_size=[1, side, side], device="cuda", prior=prior)
     model = build(args, g)
     model.train()
     # dataset: only the exemplar rows are known; place them at their dataset positions
@@ -93,6 +93,12 @@ def test_vae_step_golden(golden, fused):
 @pytest.mark.parametrize("fused", [False, True])
 def test_hvae_step_golden(golden, fused):
     _golden_step(golden("hvae_step"), "hvae_2level", fused)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_vampprior_step_golden(golden, fused):
+    """one training step under the VampPrior against the reference's own outputs."""
+    _golden_step(golden("vamp_step"), "vae", fused, prior="vampprior")
 
 
 def test_approximate_prior_golden(golden):

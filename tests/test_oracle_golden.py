@@ -88,10 +88,10 @@ def _params(g):
     return {k[2:]: torch.tensor(v).requires_grad_(True) for k, v in g.items() if k.startswith("p:")}
 
 
-def _check_step(g, model_name):
+def _check_step(g, model_name, prior="exemplar_prior"):
     side = int(g["side"])
     args = O.make_args(model_name=model_name, hidden_size=int(g["hidden"]), number_components=len(g["ex_idx"]),
-                       training_set_size=int(g["T"]), input_size=[1, side, side])
+                       training_set_size=int(g["T"]), input_size=[1, side, side], prior=prior)
     p = _params(g)
     x = torch.tensor(g["x"]); xi = torch.tensor(g["x_idx"]); ex = torch.tensor(g["exemplars"])
     ei = torch.tensor(g["ex_idx"]); beta = float(g["beta"])
@@ -123,6 +123,11 @@ def test_vae_training_step(golden):
 
 def test_hvae_training_step(golden):
     _check_step(golden("hvae_step"), "hvae_2level")
+
+
+def test_vampprior_training_step(golden):
+    """prior == 'vampprior' (per-component mean and log-variance), pinned by the reference."""
+    _check_step(golden("vamp_step"), "vae", prior="vampprior")
 
 
 def test_approximate_prior_selection(golden):
