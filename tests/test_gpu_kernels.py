@@ -178,6 +178,70 @@ def test_prior_lse_backward_vs_oracle_cfg1(ops):
     close(lg.grad, lc.grad, rtol=3e-4, atol=5e-3)
 
 
+@pytest.mark.parametrize("B,C,D,masked", [(512, 25000, 40, True), (37, 333, 24, True), (130, 5000, 63, False),
+                                          (300, 1438, 40, True), (70, 900, 128, True), (5, 3, 8, False)])
+def test_prior_lse_backward_vs_fp64_sizes(ops, B, C, D, masked):
+    """K1 backward (tensor-core path for D <= 63, FMA-pipe path above) against fp64 torch autograd of the
+    reference formula, incl. the cfg2 and cfg4-shard sizes, ragged tiles and the leave-one-out mask."""
+    g = torch.Generator().manual_seed(B + C + D)
+    mu = torch.randn(C, D, generator=g)
+    lv = torch.full((D,), -2.4189) + 0.1 * torch.randn(D, generator=g)
+    src = torch.randint(0, C, (B,), generator=g)
+    z = mu[src] + torch.exp(0.5 * lv) * torch.randn(B, D, generator=g)
+    mu_idx = torch.randint(0, 50000, (C,), generator=g)
+    z_idx = mu_idx[src].clone()
+    if masked and C <= B:       # keep at least one unmasked exemplar per row
+        z_idx = z_idx + 100000
+    gout = torch.randn(B, generator=g)
+    zd, md, ld = (t.double().requires_grad_(True) for t in (z, mu, lv))
+    lp = O.t_log_p_z_exemplar(zd, z_idx.view(-1, 1), md, ld, mu_idx, masked=masked)
+    lp.backward(gout.double())
+    zc, mc, lc = (t.cuda().requires_grad_(True) for t in (z, mu, lv))
+    got = ops.prior_lse(zc, mc, lc, z_idx.cuda() if masked else None, mu_idx.cuda() if masked else None)
+    close(got, lp.detach(), rtol=1e-4)
+    got.backward(gout.cuda())
+    for c, t in ((zc, zd), (mc, md), (lc, ld)):
+        scale = t.grad.abs().max().item()
+        close(c.grad, t.grad, rtol=1e-3, atol=5e-4 * scale)
+
+
+def test_row_block_views_backward(ops):
+    """ops.split_rows / ops.shared_rows: same values and gradients as plain slicing."""
+    g = torch.Generator().manual_seed(0)
+    t0 = torch.randn(50, 12, generator=g)
+    w1, w2 = torch.randn(20, 12, generator=g).cuda(), torch.randn(30, 12, generator=g).cuda()
+    a = t0.clone().cuda().requires_grad_(True)
+    x, y = ops.split_rows(a * 1.0, 20)
+    ((x * w1).sum() + (y * w2).sum()).backward()
+    b = t0.clone().cuda().requires_grad_(True)
+    ((b[:20] * w1).sum() + (b[20:] * w2).sum()).backward()
+    assert torch.equal(a.grad, b.grad)
+    a = t0.clone().cuda().requires_grad_(True)
+    full, head = ops.shared_rows(a * 1.0, 20)
+    wf = torch.randn(50, 12, generator=g).cuda()
+    ((full * wf).sum() + (head * w1).sum()).backward()
+    b = t0.clone().cuda().requires_grad_(True)
+    ((b * wf).sum() + (b[:20] * w1).sum()).backward()
+    close(a.grad, b.grad, rtol=1e-6)
+    # only one consumer
+    a = t0.clone().cuda().requires_grad_(True)
+    x, y = ops.split_rows(a * 1.0, 20)
+    (y * w2).sum().backward()
+    assert torch.equal(a.grad[:20], torch.zeros(20, 12, device="cuda")) and torch.equal(a.grad[20:], w2)
+
+
+def test_gemm_propagates_non_finite(ops):
+    """The in-kernel hi/lo split must not hide NaN / inf operands (they poison the affected outputs only)."""
+    x = torch.randn(300, 64, device="cuda")
+    W = torch.randn(128, 64, device="cuda") / 8
+    x[7, 3] = float("nan")
+    x[100, 9] = float("inf")
+    out = ops.linear(x, W, None)
+    bad = ~torch.isfinite(out)
+    assert bad[7].all() and bad[100].all()
+    assert int(bad.any(dim=1).sum().item()) == 2
+
+
 # ------------------------------------------------------------------ K2
 def test_knn_topk_bit_exact_golden(ops, golden):
     g = golden("knn")
