@@ -80,6 +80,9 @@ class BaseModel(nn.Module, ABC):
         self.bank_world, self.bank_rank = 1, 0
         self.grad_sync = None                       # set by distributed.shard_bank: averages the flat gradient buffer
         self.fuse_exemplar_encoder = True           # encode batch + exemplars in ONE pass of the shared trunk
+        self.overlap_prior = False                  # run the prior term on a side stream next to the decoder (AbsModel)
+        self._z_event = None
+        self._side_streams = {}
         self._resident_cache = {}
 
         if self.args.prior == 'vampprior':
@@ -381,9 +384,32 @@ class AbsModel(BaseModel):
         z_q, z_q_mean, z_q_logvar = latent_stats
         if exemplars_embedding is None and self.args.prior == 'exemplar_prior':
             exemplars_embedding = self.get_exemplar_set(z_q_mean, z_q_logvar, dataset, cache, x_indices)
-        log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+        ev, self._z_event = self._z_event, None
+        if (ev is not None and self.args.prior == 'exemplar_prior' and self.bank_group is None
+                and isinstance(exemplars_embedding, tuple)):
+            # The prior term and the decoder are independent chains between z and the loss, and the decoder's
+            # GEMMs over B rows leave most SMs idle: run K1 on a side stream forked at the point where z (and the
+            # exemplar embeddings, computed before it) became available.  Autograd replays the same fork in the
+            # backward (each node runs on its forward stream), and a capturing stream turns it into two
+            # parallel graph branches.
+            cur = torch.cuda.current_stream()
+            side = self._prior_stream()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+            cur.wait_stream(side)
+            log_p_z.record_stream(cur)
+        else:
+            log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
         log_q_z = log_normal_diag(z_q, z_q_mean, z_q_logvar, dim=1)
         return ops.lincomb((-1.0, 1.0), log_p_z, log_q_z)     # -(log_p_z - log_q_z)
+
+    def _prior_stream(self):
+        dev = torch.cuda.current_device()
+        st = self._side_streams.get(dev)
+        if st is None:
+            st = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+        return st
 
     def generate_x_from_z(self, z, with_reparameterize=True):
         generated_x, _ = self.p_x(z)
@@ -419,6 +445,8 @@ class AbsModel(BaseModel):
     def forward(self, x, label=0, num_categories=10, zq=None):
         z_q_mean, z_q_logvar = self.q_z(x) if zq is None else zq
         z_q = self.reparameterize(z_q_mean, z_q_logvar)
+        if self.overlap_prior and z_q.is_cuda:
+            self._z_event = torch.cuda.current_stream().record_event()   # fork point of the prior branch (kl_loss)
         x_mean, x_logvar = self.p_x(z_q)
         return x_mean, x_logvar, (z_q, z_q_mean, z_q_logvar)
 

@@ -53,6 +53,8 @@ constexpr int EP_BYTES = NEPI * 32 * EP_LD * 4;
 struct TcParams {
   int M, N, K, kchunk;
   int ntm, ntn, ntiles;        // tile grid: ntiles = ntn * ntm * splits, n fastest
+  int neff_last, goff_last;    // last column tile: UMMA N (16-multiple covering its valid columns) and, gated, the
+                               // row offset of the g half inside the B tile (8-multiple covering the valid h columns)
   int gated_O;
   const float* bias0; const float* bias1;
   float* out0; float* out1; float* out2; int ldc;
@@ -84,10 +86,12 @@ __device__ __forceinline__ float split_lo(float x) {
   return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xffffe000u);
 }
 
+// neff = UMMA N of this tile (BN except for a narrow last column tile: N = 300 is 2.34 tiles of 128), goff = first g row
+// / TMEM column of the gated tile's second half, bbytes = bytes TMA delivers for the B tile, last = narrow tile maps
 struct TileCoord {
-  int m0, n0, kbeg, nkb, z;
+  int m0, n0, kbeg, nkb, z, neff, goff, bbytes, last;
 };
-template <int BN, int EPI>
+template <int BN, int EPI, bool B_MN_>
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
   TileCoord c;
   const int nt = t % p.ntn;
@@ -96,6 +100,10 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
   c.z = rest / p.ntm;
   c.m0 = mt * TBM;
   c.n0 = (EPI == TC_GATED) ? nt * (BN / 2) : nt * BN;
+  c.last = nt == p.ntn - 1;
+  c.neff = c.last ? p.neff_last : BN;
+  c.goff = c.last ? p.goff_last : BN / 2;
+  c.bbytes = B_MN_ ? ((c.neff + 31) / 32) * 4096 : c.neff * 128;
   c.kbeg = c.z * p.kchunk;
   const int kend = min(p.K, c.kbeg + p.kchunk);
   c.nkb = max(0, (kend - c.kbeg + TBK - 1) / TBK);
@@ -117,12 +125,12 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
 // swizzle (no MMA reads it): one {128 m, 32 k} box, column m read by lane m without bank conflicts.
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(TTHREADS, 1)
-    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
   constexpr int A_BYTES = TBM * TBK * 4;   // 16 KB: raw A tile
   constexpr int B_BYTES = BN * TBK * 4;    // raw (= hi) B tile; the lo tile follows it
   constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   constexpr int B_OFF = A_BYTES;                         // B hi slot inside a stage
-  constexpr int RAW_BYTES = A_BYTES + B_BYTES;           // what TMA delivers per stage
   constexpr uint32_t TM_COLS = 512;                      // 2 accumulators + TSTAGES x (32 hi + 32 lo) A columns
   constexpr uint32_t TM_A0 = 2 * BN;
   static_assert(2 * BN + TSTAGES * 64 <= 512, "TMEM budget");
@@ -166,11 +174,11 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     if (lane == 0) {
       int it = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const TileCoord c = tile_coord<BN, EPI>(p, t);
+        const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
         for (int kb = 0; kb < c.nkb; ++kb, ++it) {
           const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], RAW_BYTES);
+          mbar_arrive_expect_tx(&full[s], A_BYTES + c.bbytes);
           unsigned char* sa = smem + s * STAGE_BYTES;
           unsigned char* sb = sa + B_OFF;
           const int k0 = c.kbeg + kb * TBK;
@@ -180,16 +188,18 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             tma_load_2d(sa, &tmA, &full[s], c.m0, k0);                        // box {128 m, 32 k}, no swizzle
           }
           if (!B_MN) {
-            if (EPI == TC_GATED) {                                             // box {32 k, BN/2 rows}: h rows, g rows
-              tma_load_2d(sb, &tmB, &full[s], k0, c.n0);
-              tma_load_2d(sb + (BN / 2) * 128, &tmB, &full[s], k0, p.gated_O + c.n0);
+            const CUtensorMap* mb = c.last ? &tmBl : &tmB;                     // narrow last tile: smaller boxes
+            if (EPI == TC_GATED) {                                             // box {32 k, goff rows}: h rows, g rows
+              tma_load_2d(sb, mb, &full[s], k0, c.n0);
+              tma_load_2d(sb + c.goff * 128, mb, &full[s], k0, p.gated_O + c.n0);
             } else {
-              tma_load_2d(sb, &tmB, &full[s], k0, c.n0);                      // box {32 k, BN rows}
+              tma_load_2d(sb, mb, &full[s], k0, c.n0);                        // box {32 k, neff rows}
             }
           } else {
+            const int nch = (c.neff + 31) / 32;
 #pragma unroll
             for (int q = 0; q < BN / 32; ++q)                                  // box {32 n, 32 k}
-              tma_load_2d(sb + q * 4096, &tmB, &full[s], c.n0 + 32 * q, k0);
+              if (q < nch) tma_load_2d(sb + q * 4096, &tmB, &full[s], c.n0 + 32 * q, k0);
           }
         }
       }
@@ -197,12 +207,13 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
+      constexpr uint32_t idesc_full = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
       unsigned long long w_conv = 0, w_acc = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
-        const TileCoord c = tile_coord<BN, EPI>(p, t);
+        const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
         const int acc = j & 1;
+        const uint32_t idesc = c.last ? umma_idesc(TBM, c.neff, false, B_MN) : idesc_full;
         unsigned long long t0 = tr ? gtimer() : 0;
         mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
         tc_fence_after();
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     const int am = 32 * qd + lane;                         // tile row (= TMEM lane) of this thread
     int it = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const TileCoord c = tile_coord<BN, EPI>(p, t);
+      const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
       for (int kb = 0; kb < c.nkb; ++kb, ++it) {
         const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
         mbar_wait(&full[s], ph);
@@ -261,9 +272,11 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           if (lane == 0) mbar_arrive(&conv[s]);
           continue;
         }
+        const int bchunks = c.bbytes >> 4;                   // 16-byte chunks of the B tile that hold data
         float4 vb[B_IT];
 #pragma unroll
-        for (int i = 0; i < B_IT; ++i) vb[i] = *reinterpret_cast<const float4*>(sb + (ct + CT * i) * 16);
+        for (int i = 0; i < B_IT; ++i)
+          if (ct + CT * i < bchunks) vb[i] = *reinterpret_cast<const float4*>(sb + (ct + CT * i) * 16);
         {
           uint32_t hi[16], lo[16];
           if (!A_MN) {
@@ -290,8 +303,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         }
 #pragma unroll
         for (int i = 0; i < B_IT; ++i)
-          *reinterpret_cast<float4*>(sb + B_BYTES + (ct + CT * i) * 16) =
-              make_float4(split_lo(vb[i].x), split_lo(vb[i].y), split_lo(vb[i].z), split_lo(vb[i].w));
+          if (ct + CT * i < bchunks)
+            *reinterpret_cast<float4*>(sb + B_BYTES + (ct + CT * i) * 16) =
+                make_float4(split_lo(vb[i].x), split_lo(vb[i].y), split_lo(vb[i].z), split_lo(vb[i].w));
         fence_proxy_async();        // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[s]);
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       __syncwarp();
     };
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
-      const TileCoord c = tile_coord<BN, EPI>(p, t);
+      const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
       const int acc = j & 1;
       mbar_wait(&acc_full[acc], (j >> 1) & 1);
       tc_fence_after();
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           uint32_t hv[32], gv[32];
           if (c.nkb > 0) {
             tmem_ld32(lane_addr + c0, hv);
-            tmem_ld32(lane_addr + BN / 2 + c0, gv);
+            tmem_ld32(lane_addr + c.goff + c0, gv);
             tmem_ld_wait();
           } else {
 #pragma unroll
@@ -449,7 +463,8 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, cudaStream_t st) {
+int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, TcParams& p,
+           cudaStream_t st) {
   constexpr int STAGE = TBM * TBK * 4 + 2 * BN * TBK * 4;
   constexpr int SMEM = TSTAGES * STAGE + 1024 + 256 + EP_BYTES;
   auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI>;
@@ -462,7 +477,7 @@ int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, TcPara
   p.ntm = ceil_div(g.M, TBM);
   p.ntiles = p.ntn * p.ntm * (EPI == TC_SPLITK ? g.splits : 1);
   const int grid = std::min(p.ntiles, sm_count());     // persistent: one CTA per SM
-  kern<<<grid, TTHREADS, SMEM, st>>>(ma, mb, p);
+  kern<<<grid, TTHREADS, SMEM, st>>>(ma, mb, mbl, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
@@ -507,7 +522,7 @@ int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStrea
 
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   constexpr int BN = 128;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mbl;
   // A never feeds an MMA from shared memory: an MN-major tile is one un-swizzled {128 m, 32 k} box
   int rc = g.a_mn ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
                   : make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, false);
@@ -515,6 +530,19 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   rc = make_map2d(&mb, g.b, g.b_rows, g.b_cols, g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN), g.b_mn);
   if (rc) return rc;
   TcParams p{};
+  // narrow last column tile: UMMA N = the 16-multiple that covers its valid columns (gated: both halves, 8 each)
+  if (g.epi == TC_GATED) {
+    const int h_last = g.gated_O - (ceil_div(g.gated_O, BN / 2) - 1) * (BN / 2);
+    p.goff_last = ceil_div(h_last, 8) * 8;
+    p.neff_last = 2 * p.goff_last;
+  } else {
+    const int n_last = g.N - (ceil_div(g.N, BN) - 1) * BN;
+    p.neff_last = ceil_div(n_last, 16) * 16;
+    p.goff_last = 0;
+  }
+  // K-major B: the last tile is loaded with boxes of exactly that many rows (MN-major B just loads fewer 32-wide chunks)
+  rc = make_map2d(&mbl, g.b, g.b_rows, g.b_cols, g.b_mn ? 32 : (g.epi == TC_GATED ? p.goff_last : p.neff_last), g.b_mn);
+  if (rc) return rc;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.kchunk = g.epi == TC_SPLITK ? g.kchunk : g.K;
   p.gated_O = g.gated_O;
@@ -527,10 +555,10 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.c_vec = (g.ldc % 4 == 0) && al16(g.out0) && (!g.out1 || al16(g.out1)) && (!g.out2 || al16(g.out2)) &&
             (g.epi != TC_SPLITK || ((size_t)g.M * g.ldc) % 4 == 0);
-  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, p, st);
-  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, p, st);
-  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, p, st);
-  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, ma, mb, p, st);
+  if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, mbl, p, st);
+  if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, mbl, p, st);
+  if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, mbl, p, st);
+  if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, ma, mb, mbl, p, st);
   return EXVAE_ERR_UNSUPPORTED;
 }
 

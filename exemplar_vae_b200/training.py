@@ -67,6 +67,7 @@ class GraphedTrainStep:
             from .distributed import FlatGrads
             model.flat_grads = FlatGrads(model.parameters())     # stable grad pointers, one memset per step
         ops.set_fused_grad_accumulation(True)                    # dW/db are added into the flat buffer in-kernel
+        model.overlap_prior = getattr(model, "bank_group", None) is None   # prior || decoder as parallel graph branches
         model.train()
         # eager warm-up on a side stream (allocator + optimizer state + grad buffers settle)
         s = torch.cuda.Stream()
