@@ -520,8 +520,8 @@ int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStrea
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
 
-int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
-  constexpr int BN = 128;
+template <int BN>
+static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   CUtensorMap ma, mb, mbl;
   // A never feeds an MMA from shared memory: an MN-major tile is one un-swizzled {128 m, 32 k} box
   int rc = g.a_mn ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
@@ -560,6 +560,16 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, mbl, p, st);
   if (g.epi == TC_SPLITK && g.a_mn && g.b_mn) return launch<BN, true, true, TC_SPLITK>(g, ma, mb, mbl, p, st);
   return EXVAE_ERR_UNSUPPORTED;
+}
+
+int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
+  // Small GEMMs (the decoder and the batch-only heads: a few 128-wide tiles) are latency-bound and leave most SMs idle:
+  // 64-wide tiles double the number of CTAs and halve each CTA's B-side work and epilogue.
+  if (g.epi != TC_SPLITK) {
+    const int ntn = g.epi == TC_GATED ? ceil_div(g.gated_O, 64) : ceil_div(g.N, 128);
+    if (2 * ceil_div(g.M, TBM) * ntn <= sm_count()) return tc_gemm_launch_bn<64>(g, st);
+  }
+  return tc_gemm_launch_bn<128>(g, st);
 }
 
 }  // namespace exvae
