@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_full = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
       unsigned long long w_conv = 0, w_acc = 0;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(x_full, nkb * 2 * BT_BOX);
       for (int kb = 0; kb < nkb; ++kb)
         for (int pl = 0; pl < 2; ++pl) tma_load_3d(sX + (kb * 2 + pl) * BT_BOX, &tmX, x_full, kb * 32, xi * 128, pl);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc_s = umma_idesc(128, 128, false, false);
       const uint32_t idesc_g = umma_idesc(128, p.NG, false, false);
       mbar_wait(x_full, 0);

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(a_full, nkb * 2 * PT_TILE_BYTES);
       for (int kb = 0; kb < nkb; ++kb)
         for (int pl = 0; pl < 2; ++pl) tma_load_3d(sA + (kb * 2 + pl) * PT_TILE_BYTES, &tmZ, a_full, kb * 32, rb * 128, pl);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc(128, PT_BN, false, false);
       mbar_wait(a_full, 0);
       for (int t = t0; t < t1; ++t) {
