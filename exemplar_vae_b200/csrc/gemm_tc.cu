@@ -60,8 +60,7 @@ struct TcParams {
   float* out0; float* out1; float* out2; int ldc;
   int act; float lo, hi;
   int c_vec;
-  unsigned long long* trace;   // debug: per-CTA timeline (tools/gemm_trace.py), null in production
-  int dbg;                     // debug (EXVAE_GEMM_DEBUG): 1 no MMAs, 2 no conversion, 4 one product, 32 no epilogue stores
+  unsigned long long* trace;   // debug: per-CTA {start, end, tiles, SM} (tools/gemm_trace.py), null in production
 };
 unsigned long long* g_trace = nullptr;
 
@@ -209,22 +208,17 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     if (elect_one_sync()) {
       constexpr uint32_t idesc_full = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
-      unsigned long long w_conv = 0, w_acc = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
         const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
         const int acc = j & 1;
         const uint32_t idesc = c.last ? umma_idesc(TBM, c.neff, false, B_MN) : idesc_full;
-        unsigned long long t0 = tr ? gtimer() : 0;
         mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
         tc_fence_after();
-        if (tr) w_acc += gtimer() - t0;
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < c.nkb; ++kb, ++it) {
           const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
-          if (tr) t0 = gtimer();
           mbar_wait(&conv[s], ph);
           tc_fence_after();
-          if (tr) w_conv += gtimer() - t0;
           const uint32_t sb_hi = smem_u32(smem + s * STAGE_BYTES) + B_OFF;
           const uint32_t sb_lo = sb_hi + B_BYTES;
           const uint32_t ta_hi = tmem_base + TM_A0 + (uint32_t)(s * 64);
@@ -236,10 +230,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             const uint32_t boff = B_MN ? ks * 1024 : ks * 32;
             const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
-            if (p.dbg & 1) continue;
             const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
             umma_tf32_ts(d_tmem, ta_hi + 32 + 8 * ks, b_hi, idesc, first);           // A_lo x B_hi: small terms first
-            if (p.dbg & 4) continue;
             umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_lo, idesc, 1u);                   // A_hi x B_lo
             umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, 1u);                   // A_hi x B_hi
           }
@@ -248,7 +240,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         if (c.nkb > 0) umma_commit(&acc_full[acc]);   // accumulator complete
         else mbar_arrive(&acc_full[acc]);
       }
-      if (tr) { tr[2] = j; tr[3] = w_conv; tr[5] = w_acc; }
+      if (tr) tr[2] = j;
     }
   } else if (warp < EPI_WARP0) {
     // ---------------------------------------------------------------- converters (warps 2..9)
@@ -267,11 +259,6 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         mbar_wait(&full[s], ph);
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + B_OFF;
-        if (p.dbg & 2) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&conv[s]);
-          continue;
-        }
         const int bchunks = c.bbytes >> 4;                   // 16-byte chunks of the B tile that hold data
         float4 vb[B_IT];
 #pragma unroll
@@ -320,11 +307,10 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     const int q = warp & 3;       // TMEM lane quadrant this warp may access
     float* patch = reinterpret_cast<float*>(smem + TSTAGES * STAGE_BYTES + 256) + (warp - EPI_WARP0) * (32 * EP_LD);
     int j = 0;
-    unsigned long long busy = 0;
     // write the staged 32x32 patch to dst[(row0 + r) * ldc + col0 + c] for c < ncols
     auto flush = [&](float* dst, int row0, int col0, int ncols) {
       __syncwarp();
-      if (p.c_vec && !(p.dbg & 32)) {
+      if (p.c_vec) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + (lane >> 3), ch = (lane & 7) * 4;
@@ -340,7 +326,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             }
           }
         }
-      } else if (!(p.dbg & 32)) {
+      } else {
         if (lane < ncols)
           for (int r = 0; r < 32 && row0 + r < p.M; ++r) dst[(size_t)(row0 + r) * p.ldc + col0 + lane] = patch[r * EP_LD + lane];
       }
@@ -351,7 +337,6 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       const int acc = j & 1;
       mbar_wait(&acc_full[acc], (j >> 1) & 1);
       tc_fence_after();
-      const unsigned long long t0 = tr ? gtimer() : 0;
       const int row0 = c.m0 + 32 * q;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
       float* prow = patch + lane * EP_LD;
@@ -437,9 +422,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (tr) busy += gtimer() - t0;
     }
-    if (tr && warp == EPI_WARP0 && lane == 0) tr[4] = busy;
   }
   tc_fence_before();
   __syncthreads();
@@ -550,8 +533,6 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   p.act = g.act; p.lo = g.lo; p.hi = g.hi;
   p.trace = g_trace;
   if (g_trace) g_trace += 8 * 160;   // the next traced launch writes the next segment
-  static const int dbg_env = [] { const char* e = getenv("EXVAE_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
-  p.dbg = dbg_env;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.c_vec = (g.ldc % 4 == 0) && al16(g.out0) && (!g.out1 || al16(g.out1)) && (!g.out2 || al16(g.out2)) &&
             (g.epi != TC_SPLITK || ((size_t)g.M * g.ldc) % 4 == 0);

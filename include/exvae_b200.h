@@ -167,10 +167,10 @@ EXVAE_API int exvae_linear_bwd(const float* x, const float* W, const float* out,
                      void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream);
 /* 1 = tcgen05 3xTF32 backend active on the current device, 0 = fp32 FMA-pipe backend */
 EXVAE_API int exvae_gemm_backend(void);
-/* Debug / profiling aid (tools/gemm_trace.py): when buf != NULL every (persistent) CTA of the following
- * tensor-core GEMM launches writes 8 uint64 at buf[8*(160*launch + blockIdx.x)]: {globaltimer at start, -, tiles
- * done, ns the MMA warp waited for converted operands, ns the epilogue warp was busy, ns the MMA warp waited for
- * a free accumulator, globaltimer at end, SM id}; NULL switches tracing off. */
+/* Debug / profiling aid (tools/gemm_trace.py, tools/prior_trace.py): when buf != NULL every CTA of the following
+ * tensor-core launches writes 8 uint64 of %globaltimer stamps into the launch's segment of buf (GEMM: 160 CTAs x 8
+ * words per launch: {start, -, tiles done, -, -, -, end, SM id}; prior backward: 400 x 8 words per pass, see
+ * prior_bwd_tc.cu); NULL switches tracing off.  Keep the stamps out of hot loops: a %globaltimer read is slow. */
 EXVAE_API int exvae_gemm_set_trace(uint64_t* buf);
 
 /* ---------------------------------------------------------------- convolution support (K4)

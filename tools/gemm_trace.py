@@ -32,9 +32,6 @@ def summarize(name, buf, launch):
     print(f"{name}: {len(t)} persistent CTAs, kernel span {span:.1f} us; per CTA (median / max):")
     print(f"   tiles per CTA                      {np.median(t[:, 2]):8.0f} {t[:, 2].max():8.0f}")
     print(f"   CTA lifetime (us)                  {np.median(life):8.2f} {life.max():8.2f}")
-    print(f"   MMA warp waiting for converters    {np.median(t[:, 3]) / 1e3:8.2f} {t[:, 3].max() / 1e3:8.2f}")
-    print(f"   MMA warp waiting for accumulator   {np.median(t[:, 5]) / 1e3:8.2f} {t[:, 5].max() / 1e3:8.2f}")
-    print(f"   epilogue warp busy                 {np.median(t[:, 4]) / 1e3:8.2f} {t[:, 4].max() / 1e3:8.2f}")
 
 
 def timed(fn, n=20):
@@ -61,7 +58,6 @@ L.exvae_gemm_set_trace(None)
 summarize(f"gated fwd R={R} K={K} O={O}", buf, 0)
 summarize("gated bwd dx", buf, 1)
 summarize("gated bwd dW", buf, 2)
-print("debug mode %s" % os.environ.get("EXVAE_GEMM_DEBUG", "0"))
 print("fwd entry point: %.1f us per call" % timed(lambda: ops.gated_dense(x, Wh, b, Wg, b)))
 
 
