@@ -83,6 +83,7 @@ class BaseModel(nn.Module, ABC):
         self.overlap_prior = False                  # run the prior term on a side stream next to the decoder (AbsModel)
         self._z_event = None
         self._side_streams = {}
+        self._zero_rows = {}
         self._resident_cache = {}
 
         if self.args.prior == 'vampprior':
@@ -175,6 +176,26 @@ class BaseModel(nn.Module, ABC):
         return ops.reparameterize(mu, logvar.expand_as(mu), eps)
 
     # ------------------------------------------------------------------ exemplar prior
+    def _bank_logvar_row(self, center_log_variance):
+        """Row 0 of the bank's log-variance (models/BaseModel.py:101).  When the bank is the learned scalar broadcast
+        (q_z(prior=True): a stride-0 view of ``prior_log_variance``) the row is taken from the parameter directly:
+        autograd's select + expand backward would otherwise zero-fill a [C,D] tensor and reduce it again."""
+        if center_log_variance.dim() != 2:
+            return center_log_variance
+        plv = getattr(self, "prior_log_variance", None)
+        if (plv is not None and center_log_variance.stride() == (0, 0)
+                and center_log_variance.data_ptr() == plv.data_ptr()):
+            return plv.expand(center_log_variance.shape[1])
+        return center_log_variance[0, :]
+
+    def _zeros_row(self, P, device):
+        """[1,P] zeros (x_logvar of a Bernoulli decoder, models/AbsModel.py:38), allocated once per device."""
+        key = (P, str(device))
+        z = self._zero_rows.get(key)
+        if z is None:
+            z = self._zero_rows[key] = torch.zeros(1, P, device=device)
+        return z
+
     def log_p_z_exemplar(self, z, z_indices, exemplars_embedding, test):
         """models/BaseModel.py:98-109 — the [B,C] matrix (materialising, no autograd)."""
         centers, center_log_variance, center_indices = exemplars_embedding
@@ -222,7 +243,7 @@ class BaseModel(nn.Module, ABC):
             if not sum:
                 return self.log_p_z_exemplar(z, z_indices, exemplars_embedding, test)
             centers, center_log_variance, center_indices = exemplars_embedding
-            lv = center_log_variance[0, :] if center_log_variance.dim() == 2 else center_log_variance
+            lv = self._bank_logvar_row(center_log_variance)
             masked = (test is False) and (self.args.no_mask is False) and z_indices is not None
             c_total = getattr(exemplars_embedding, "c_total", None)
             if c_total is not None and self.bank_group is not None:     # range-sharded bank (distributed.py)
@@ -437,7 +458,7 @@ class AbsModel(BaseModel):
             if self.args.input_type != 'binary' and self.args.use_logit is False:
                 x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
         if self.args.input_type == 'binary':
-            x_logvar = torch.zeros(1, P, device=x_mean.device)
+            x_logvar = self._zeros_row(P, x_mean.device)
         else:
             x_logvar = self.decoder_logstd.expand(x_mean.shape[0], P)
         return x_mean.reshape(-1, P), x_logvar.reshape(-1, P)
@@ -499,7 +520,7 @@ class BaseHModel(BaseModel):
         if conv:
             x_mean = flat_chw(x_mean)
         if self.args.input_type == 'binary':
-            x_logvar = torch.zeros(1, P, device=x_mean.device)
+            x_logvar = self._zeros_row(P, x_mean.device)
         else:
             x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
             x_logvar = self.p_x_logvar(h_decoder)

@@ -94,7 +94,11 @@ class GraphedTrainStep:
             self.model.grad_sync()                 # data-parallel: one all-reduce of the flat gradient buffer
         self.opt.step()
         with torch.no_grad():
-            self.out.copy_(torch.stack((loss.detach(), RE.detach(), KL.detach())))
+            base = loss._base            # calculate_loss(average=True) returns three views of one [3] tensor
+            if base is not None and base.numel() == 3 and RE._base is base and KL._base is base:
+                self.out.copy_(base.detach())
+            else:
+                self.out.copy_(torch.stack((loss.detach(), RE.detach(), KL.detach())))
 
     def step(self, data=None, indices=None):
         if data is not None:
