@@ -33,3 +33,11 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     return load
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    """Every test starts from the same CPU / CUDA default-generator state, whatever ran before it."""
+    import torch
+    torch.manual_seed(0)
+    yield
