@@ -415,9 +415,11 @@ class AbsModel(BaseModel):
             # parallel graph branches.
             cur = torch.cuda.current_stream()
             side = self._prior_stream()
+            centers, clv, cidx = exemplars_embedding
+            emb = (centers, self._bank_logvar_row(clv), cidx)     # the parameter's view is taken on this stream
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+                log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=emb)
             cur.wait_stream(side)
             log_p_z.record_stream(cur)
         else:
