@@ -318,7 +318,8 @@ struct AdamRec {
 // bumps the step counter.  The update kernel adds the ADAM_NCH partials in a fixed order.
 constexpr int ADAM_NCH = 16;
 __global__ void __launch_bounds__(256) adam_norm_kernel(const AdamRec* __restrict__ table, float* __restrict__ norms,
-                                                        int64_t* __restrict__ step) {
+                                                        int64_t* __restrict__ step, float lr, float beta1, float beta2,
+                                                        float* __restrict__ step_size_out) {
   __shared__ float sh[8];
   const AdamRec rec = table[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -336,20 +337,24 @@ __global__ void __launch_bounds__(256) adam_norm_kernel(const AdamRec* __restric
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sh[i];
     norms[blockIdx.x * ADAM_NCH + blockIdx.y] = t;
-    if (blockIdx.x == 0 && blockIdx.y == 0) step[0] += 1;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      // bump the step counter and evaluate the bias-corrected step size ONCE (fp64 pow), not in every update thread
+      const long long ts = step[0] + 1;
+      step[0] = ts;
+      const double bc1 = 1.0 - pow((double)beta1, (double)ts), bc2 = 1.0 - pow((double)beta2, (double)ts);
+      *step_size_out = (float)((double)lr * sqrt(bc2) / bc1);
+    }
   }
 }
 __global__ void __launch_bounds__(256) adam_update_kernel(const AdamRec* __restrict__ table,
                                                           const float* __restrict__ norms,
-                                                          const int64_t* __restrict__ step, float lr, float beta1,
+                                                          const float* __restrict__ step_size_in, float beta1,
                                                           float beta2, float eps, float wd) {
   const AdamRec rec = table[blockIdx.y];
   if (!rec.g) return;
   const long long base = (long long)blockIdx.x * blockDim.x * 4;
   if (base >= rec.n) return;
-  const double t = (double)step[0];
-  const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
-  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  const float step_size = *step_size_in;
   float nsq = 0.f;
 #pragma unroll
   for (int i = 0; i < ADAM_NCH; ++i) nsq += norms[blockIdx.y * ADAM_NCH + i];
@@ -491,9 +496,10 @@ extern "C" int exvae_adam_normgrad_step(const int64_t* table, int n_tensors, int
   static_assert(sizeof(AdamRec) == 5 * sizeof(int64_t), "table record is 5 x int64");
   cudaStream_t st = as_stream(stream);
   const AdamRec* recs = reinterpret_cast<const AdamRec*>(table);
-  adam_norm_kernel<<<dim3(n_tensors, ADAM_NCH), 256, 0, st>>>(recs, norms, step);
+  float* step_size = norms + (size_t)n_tensors * ADAM_NCH;      // one extra float behind the partial norms
+  adam_norm_kernel<<<dim3(n_tensors, ADAM_NCH), 256, 0, st>>>(recs, norms, step, lr, beta1, beta2, step_size);
   EXVAE_CUDA(cudaGetLastError());
   dim3 grid((unsigned)((max_numel + 1023) / 1024), n_tensors);
-  adam_update_kernel<<<grid, 256, 0, st>>>(recs, norms, step, lr, beta1, beta2, eps, weight_decay);
+  adam_update_kernel<<<grid, 256, 0, st>>>(recs, norms, step_size, beta1, beta2, eps, weight_decay);
   EXVAE_RETURN_LAST_ERROR();
 }

@@ -38,7 +38,7 @@ class AdamNormGrad(Optimizer):
             ent = {
                 'key': key,
                 'table': torch.tensor(rows, dtype=torch.int64).to(dev),
-                'norms': torch.empty(16 * len(rows), dtype=torch.float32, device=dev),
+                'norms': torch.empty(16 * len(rows) + 4, dtype=torch.float32, device=dev),   # 16 partials per tensor + step size
                 'step': (ent['step'] if ent is not None else
                          torch.full((1,), int(self.state[group['params'][0]].get('step', 0)), dtype=torch.int64,
                                     device=dev)),

@@ -245,7 +245,8 @@ EXVAE_API int exvae_rng_advance(uint64_t* counter, uint64_t by, exvae_stream_t s
  * One fused multi-tensor step: per-tensor g / (||g||_2 + 1e-7), Adam moments, bias correction
  * from the device step counter (incremented by the call), parameter update.
  * table: device array of n_tensors records {param*, grad*, exp_avg*, exp_avg_sq*, numel} laid out
- * as 5 x int64 per tensor.  norms: scratch [16 * n_tensors] fp32.  step: device int64[1].            */
+ * as 5 x int64 per tensor.  norms: scratch [16 * n_tensors + 1] fp32 (16 partial squared
+ * norms per tensor + the step size).  step: device int64[1].                                                   */
 EXVAE_API int exvae_adam_normgrad_step(const int64_t* table, int n_tensors, int64_t max_numel, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int64_t* step, float* norms,
                              exvae_stream_t stream);
