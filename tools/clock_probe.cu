@@ -1,3 +1,4 @@
+// %globaltimer vs clock64 calibration (build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/clock_probe tools/clock_probe.cu)
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }

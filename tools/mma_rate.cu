@@ -1,9 +1,10 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/mma_rate tools/mma_rate.cu -lcuda   (run on a B200)
 // Micro-benchmark: how fast can ONE thread issue tcgen05.mma.kind::tf32, and how long does the tensor pipe take per
 // instruction, for N = 64 / 128 / 256 with A from shared memory or from tensor memory?
 #include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include "../../exemplar_vae_b200/csrc/tc_common.cuh"
+#include "../exemplar_vae_b200/csrc/tc_common.cuh"
 using namespace exvae;
 using namespace exvae::tc;
 namespace exvae { int sm_count() { return 148; } }
