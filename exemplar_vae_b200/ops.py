@@ -97,7 +97,7 @@ class _PriorLSE(torch.autograd.Function):
         stats = torch.empty((B, 4), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(stats), _p(ws),
                                       ws.numel(), _stream()), "prior_lse_fwd")
-        _count(3)
+        _count(4 if (z_idx is not None and mu_idx is not None) else 3)   # stage, [mask list], main, merge
         G = 1
         all_stats = stats
         if group is not None:
@@ -126,7 +126,7 @@ class _PriorLSE(torch.autograd.Function):
         dlv = torch.empty((D,), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_bwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(lse2), _p(g),
                                       _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _stream()), "prior_lse_bwd")
-        _count(3)
+        _count(5 if D <= 63 else 3)   # tensor-core path: prep, two passes, rows, dlogvar; FMA path: main, rows, dlogvar
         return dz, dmu, dlv.view_as(logvar), None, None, None, None
 
 
