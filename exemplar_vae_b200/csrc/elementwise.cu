@@ -85,18 +85,21 @@ __global__ void __launch_bounds__(256) lognormstd_bwd_kernel(const float* __rest
     dx[e] = -dout[e / D] * x[e];
 }
 
-__global__ void __launch_bounds__(256) bernoulli_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+// one block of 128 threads per row: 512 rows x 784 pixels with two logf each is latency-bound with a warp per row
+__global__ void __launch_bounds__(128) bernoulli_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                             int B, int P, float* __restrict__ out) {
-  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
+  __shared__ float sh[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   float a = 0.f;
-  for (int d = lane; d < P; d += 32) {
+  for (int d = tid; d < P; d += 128) {
     const size_t o = (size_t)b * P + d;
     const float p = fminf(fmaxf(mean[o], kMinEps), kMaxEps), xv = x[o];
     a += xv * logf(p) + (1.f - xv) * logf(1.f - p);
   }
   a = warp_sum(a);
-  if (lane == 0) out[b] = a;
+  if (lane == 0) sh[warp] = a;
+  __syncthreads();
+  if (tid == 0) out[b] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
 __global__ void __launch_bounds__(256) bernoulli_bwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ dout, long long n, int P,
@@ -426,7 +429,8 @@ extern "C" int exvae_log_normal_standard_bwd(const float* x, const float* dout, 
 extern "C" int exvae_log_bernoulli_fwd(const float* x, const float* mean, int B, int P, float* out,
                                        exvae_stream_t stream) {
   EXVAE_CHECK_ARG(x && mean && out && B > 0 && P > 0);
-  ROW_LAUNCH(bernoulli_fwd_kernel, B, x, mean, B, P, out);
+  bernoulli_fwd_kernel<<<B, 128, 0, as_stream(stream)>>>(x, mean, B, P, out);
+  EXVAE_RETURN_LAST_ERROR();
 }
 extern "C" int exvae_log_bernoulli_bwd(const float* x, const float* mean, const float* dout, int B, int P,
                                        float* dmean, exvae_stream_t stream) {
