@@ -96,3 +96,42 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("against the oracle", ""), fn
+
+
+def test_row_block_views_autograd_cpu():
+    """ops.split_rows / ops.shared_rows are pure autograd plumbing (no kernel): same values and gradients as slicing."""
+    import torch
+    from exemplar_vae_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    t0 = torch.randn(50, 12, generator=g)
+    w1, w2, wf = torch.randn(20, 12, generator=g), torch.randn(30, 12, generator=g), torch.randn(50, 12, generator=g)
+    a = t0.clone().requires_grad_(True)
+    x, y = ops.split_rows(a * 1.0, 20)
+    assert torch.equal(x, t0[:20]) and torch.equal(y, t0[20:])
+    ((x * w1).sum() + (y * w2).sum()).backward()
+    b = t0.clone().requires_grad_(True)
+    ((b[:20] * w1).sum() + (b[20:] * w2).sum()).backward()
+    assert torch.equal(a.grad, b.grad)
+    a = t0.clone().requires_grad_(True)
+    full, head = ops.shared_rows(a * 1.0, 20)
+    ((full * wf).sum() + (head * w1).sum()).backward()
+    b = t0.clone().requires_grad_(True)
+    ((b * wf).sum() + (b[:20] * w1).sum()).backward()
+    assert torch.allclose(a.grad, b.grad, rtol=1e-6, atol=0)
+    a = t0.clone().requires_grad_(True)
+    x, y = ops.split_rows(a * 1.0, 20)
+    (y * w2).sum().backward()                      # only one consumer: the other block's gradient is zero
+    assert torch.equal(a.grad[:20], torch.zeros(20, 12)) and torch.equal(a.grad[20:], w2)
+
+
+def test_workspace_sizes_cover_the_tensor_core_plans(L):
+    """Host-side planning (no device needed): workspaces grow with the problem and hold the transposed planes of the
+    tensor-core K1 backward (2 x NG x (Bpad + Cpad) floats on top of the forward's)."""
+    fwd = L.exvae_prior_lse_fwd_workspace_bytes(512, 25000, 40)
+    both = L.exvae_prior_lse_workspace_bytes(512, 25000, 40)
+    assert both - fwd >= 2 * 48 * (512 + 25088) * 4
+    assert L.exvae_dense_fwd_workspace_bytes(25512, 784, 300, 1) >= 600 * 784 * 4     # [Wh ; Wg] as one operand
+    assert L.exvae_dense_fwd_workspace_bytes(25512, 300, 40, 0) == 0                   # linear layers read x and W in place
+    small = L.exvae_gated_dense_bwd_workspace_bytes(512, 300, 300)
+    big = L.exvae_gated_dense_bwd_workspace_bytes(25512, 300, 300)
+    assert big > small > 512 * 600 * 4
