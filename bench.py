@@ -32,8 +32,8 @@ CFG = dict(model_name="vae", T=50000, N=25000, B=512, D=40, H=300, P=784)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)      # ~0.26 s timed: a few clock samples fall inside
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="exvae_b200", choices=["exvae_b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--exemplars", type=int, default=CFG["N"])
@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
