@@ -1,7 +1,7 @@
 """Multi-GPU parity check (run under torchrun on N GPUs): a training step with the exemplar bank
 range-sharded over the ranks must reproduce the single-GPU step over the concatenated batch.
 
-  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/manual/mgpu_check.py
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import exemplar_vae_b200 as E  # noqa: E402
 from exemplar_vae_b200 import distributed as D  # noqa: E402
 from oracle import exvae_oracle as O  # noqa: E402

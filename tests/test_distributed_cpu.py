@@ -1,6 +1,6 @@
 """world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: shard ranges, the associative
 merge of per-shard log-sum-exp partials after an all-gather, and the flat gradient all-reduce.
-The CUDA kernels themselves are covered by the -m gpu tests and tools/mgpu_check.py."""
+The CUDA kernels themselves are covered by the -m gpu tests and tests/manual/mgpu_check.py."""
 import os
 import socket
 
