@@ -291,7 +291,7 @@ def run_gpu(a):
                     "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": traffic, "peak_source": peak_src, "ms_per_launch": prior_ms,
                     "model": "algorithmic bytes = B*N*D*2 per call (north_star / SURVEY 8d streaming model, B and N per "
-                             "rank); compulsory DRAM traffic is ~5 MB because bank tiles are reused from shared "
+                             "rank); measured DRAM traffic is ~10 MB (the staged hi/lo planes of the bank, read once) because tiles are reused from shared "
                              "memory/L2, so frac > 1 is expected; the true limiter is the MUFU/ALU rate of the soft-max "
                              "epilogue plus fixed launch/staging latency at this size"}
     gemm_ms = sum(v for k, v in breakdown.items() if "dense" in k or "linear" in k)
