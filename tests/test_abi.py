@@ -135,3 +135,19 @@ def test_workspace_sizes_cover_the_tensor_core_plans(L):
     small = L.exvae_gated_dense_bwd_workspace_bytes(512, 300, 300)
     big = L.exvae_gated_dense_bwd_workspace_bytes(25512, 300, 300)
     assert big > small > 512 * 600 * 4
+
+
+def test_vampprior_state_dict_keys_match_the_reference(golden):
+    """prior == 'vampprior': same parameter names and shapes as the reference model that produced the golden
+    (means.linear.weight [P, C] for the pseudo-inputs; idle_input is not part of the state_dict there either)."""
+    import exemplar_vae_b200 as E
+    from oracle import exvae_oracle as O
+    g = golden("vamp_step")
+    side = int(g["side"])
+    args = O.make_args(model_name="vae", prior="vampprior", hidden_size=int(g["hidden"]), number_components=len(g["ex_idx"]),
+                       training_set_size=int(g["T"]), input_size=[1, side, side])
+    model = E.importing_model(args)(args)
+    want = {k[2:]: tuple(v.shape) for k, v in g.items() if k.startswith("p:")}
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == want
+    assert "prior_log_variance" not in got and got["means.linear.weight"] == (side * side, len(g["ex_idx"]))
