@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py — training-step throughput of the Exemplar-VAE hot path on B200.
 
-Workload (BASELINE.json configs[1]): model_name=vae + exemplar_prior, synthetic dynamic-MNIST
+Default workload = BASELINE.json configs[1]: model_name=vae + exemplar_prior, synthetic dynamic-MNIST
 shaped data (T=50 000 x 784 ~ U(0,1), Bernoulli-binarised batches), N=25 000 exemplars re-sampled
-every step and encoded WITH gradient, D=40, batch 512 per GPU.  One "step" = the loop body of
-the reference's utils/training.py:27-46: binarise, calculate_loss, backward, AdamNormGrad step.
+every step and encoded WITH gradient, D=40, batch 512 per GPU.  One "step" = the loop body of the
+reference's utils/training.py:27-46: binarise, calculate_loss, backward, AdamNormGrad step.
 
     python bench.py --gpus N --steps K --warmup W            (own arm; torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  (CPU oracle port of the same step)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU loop, oracle/_ref)
+    python bench.py --config cfg3|cfg4|cfg5 ...              (the other BASELINE.json configs)
+    python bench.py --scaling strong --gpus N ...            (global batch fixed, split over N ranks)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every key.
 """
@@ -25,30 +27,80 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "training-step imgs/sec (N=25k exemplar prior); prior-kernel HBM GB/s in roofline"
-CFG = dict(model_name="vae", T=50000, N=25000, B=512, D=40, H=300, P=784)
+METRIC = "training-step imgs/sec (N=25k exemplar prior); prior-kernel HBM GB/s in roofline_prior"
+
+# BASELINE.json `configs` (index = position in that list); cfg2 is the one the metric is quoted on
+CONFIGS = {
+    "cfg1": dict(model="vae", batch=100, exemplars=1000, train_size=50000, input="1x28x28", approximate=False,
+                 note="BASELINE configs[0]: vae, N=1000, batch 100 (the reference's CPU-runnable plumbing case)"),
+    "cfg2": dict(model="vae", batch=512, exemplars=25000, train_size=50000, input="1x28x28", approximate=False,
+                 note="BASELINE configs[1]: vae, dynamic-MNIST shaped, N=25000, D=40, batch 512"),
+    "cfg3": dict(model="convhvae_2level", batch=100, exemplars=25000, train_size=50000, input="1x28x28",
+                 approximate=True,
+                 note="BASELINE configs[2]: convhvae_2level, fashion-MNIST shaped, N=25000 candidates, kNN cache k=10"),
+    "cfg4": dict(model="hvae_2level", batch=256, exemplars=11500, train_size=23000, input="1x28x28",
+                 approximate=False,
+                 note="BASELINE configs[3]: hvae_2level, omniglot shaped, N=11500, batch 256, bank sharded over the ranks"),
+    "cfg5": dict(model="single_conv", batch=64, exemplars=100000, train_size=100000, input="3x64x64",
+                 approximate=True,
+                 note="BASELINE configs[4]: fully_conv (model_name=single_conv) on synthetic 64x64x3; declared variant "
+                      "(SURVEY §7): the architecture ties D to bottleneck*16*16 at 64x64 (D=128 is unreachable), so the "
+                      "training step runs the model's own latent (bottleneck 2 -> D=512) in kNN mode over N=100000 "
+                      "cached exemplars, and the N=100000 x D=128 exemplar bank is measured by the prior-kernel leg "
+                      "(`prior_bank`), range-sharded over the ranks"),
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)      # ~0.26 s timed: a few clock samples fall inside
+    ap.add_argument("--steps", type=int, default=300)      # ~0.25 s timed at cfg2: a few clock samples fall inside
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="exvae_b200", choices=["exvae_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=CFG["B"])
-    ap.add_argument("--exemplars", type=int, default=CFG["N"])
-    ap.add_argument("--train-size", type=int, default=CFG["T"])
-    ap.add_argument("--model", default=CFG["model_name"], choices=["vae", "hvae_2level"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (weak) / global batch (strong)")
+    ap.add_argument("--exemplars", type=int, default=None)
+    ap.add_argument("--train-size", type=int, default=None)
+    ap.add_argument("--model", default=None, choices=["vae", "hvae_2level", "convhvae_2level", "single_conv"])
+    ap.add_argument("--input", default=None, help="CxHxW")
+    ap.add_argument("--approximate-prior", dest="approximate", action="store_true", default=None)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-vs-single parity check at N>1")
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    for k in ("model", "batch", "exemplars", "input", "approximate"):
+        if getattr(a, k) is None:
+            setattr(a, k, c[k])
+    if a.train_size is None:
+        a.train_size = c["train_size"]
+    a.chw = [int(v) for v in a.input.lower().split("x")]
+    a.P = a.chw[0] * a.chw[1] * a.chw[2]
+    if a.config in ("cfg3", "cfg5") and a.steps == 300:
+        a.steps = 40                                       # conv steps are ~10-100x longer than the MLP ones
+    return a
+
+
+def model_kwargs(a):
+    """Namespace overrides of the reference CLI (density_estimation.py:27-93) for this workload."""
+    kw = dict(model_name=a.model, number_components=a.exemplars, training_set_size=a.train_size,
+              input_size=list(a.chw), approximate_prior=bool(a.approximate), approximate_k=a.k)
+    if a.model == "single_conv":
+        d = 2 * (a.chw[1] // 4) * (a.chw[2] // 4)         # latent = bottleneck x H/4 x W/4 (models/AbsModel.py:33)
+        kw.update(input_type="continuous", bottleneck=2, z1_size=d, z2_size=d, dataset_name="celeba",
+                  dynamic_binarization=False)
+    if a.model == "convhvae_2level":
+        kw.update(dataset_name="fashion_mnist")
+    return kw
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json, burst)"
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
@@ -94,22 +146,58 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_config(a, world):
+    per_gpu = a.batch if a.scaling == "weak" else a.batch // world
+    mode = (f"kNN mode (approximate_prior, k={a.k}, cache of T rows, <= B*k exemplars re-encoded with grad)"
+            if a.approximate else "exact prior, all N exemplars re-drawn and encoded with grad every step")
+    return {"workload": f"{a.config}: {a.model}+exemplar_prior, synthetic {a.input} images, T={a.train_size}, "
+                        f"N={a.exemplars} exemplars/step ({mode}), batch {per_gpu}/GPU",
+            "baseline_config": CONFIGS[a.config]["note"],
+            "global_batch": per_gpu * world,
+            "bank": ("replicated" if world == 1 else
+                     ("data-parallel replicas (kNN cache per rank)" if a.approximate else "range-sharded over ranks")),
+            "l2": "per-step working set (activations + the exemplar gather) exceeds the 126 MB L2; no explicit flush",
+            "cuda_graph": not a.no_graph}
+
+
 # ----------------------------------------------------------------------------------------- CPU
-def cpu_reference_run(a, steps, warmup, budget_s=240.0):
-    """The reference's training step restated on CPU (oracle port, torch-CPU, all host threads)."""
+def synthetic_data(a):
     import torch
-    from oracle import exvae_oracle as O
+    g = torch.Generator().manual_seed(1234)
+    return torch.rand(a.train_size, a.P, generator=g)
+
+
+def cpu_reference_run(a, batch, steps, warmup, budget_s=30.0):
+    """The reference's training step on the host cores: the UNMODIFIED reference loop from oracle/_ref when the
+    recipe has vendored it (kind "reference"), else the oracle port (kind "port"; MLP models only)."""
+    import torch
     cores = os.cpu_count() or 1
+    from oracle import ref_runner
+    if ref_runner.available():
+        import contextlib
+        import io
+        args = ref_runner.ref_args(**model_kwargs(a))
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            r = ref_runner.run_steps(args, synthetic_data(a), batch, steps, warmup, cores, budget_s=budget_s)
+        ms = r["ms_per_step"]
+        sample = (f"{r['steps']} full steps of the same workload (B={batch}, N={a.exemplars}, T={a.train_size}) after "
+                  f"{r['warmup']} warm-up through the reference's own utils/training.py:train_one_epoch + models + "
+                  f"AdamNormGrad (unmodified, oracle/_ref), torch-CPU, {cores} threads"
+                  + (f"; per-epoch cache_z ({r['cache_z_s']:.1f} s) excluded" if a.approximate else ""))
+        return {"value": batch / (ms / 1e3), "ms_per_step": ms, "steps": r["steps"], "cores": cores,
+                "kind": "reference", "sample": sample}
+    from oracle import exvae_oracle as O
+    if a.model not in ("vae", "hvae_2level") or a.approximate:
+        raise RuntimeError("oracle/_ref is missing and the oracle port only covers the exact-prior MLP step")
     torch.set_num_threads(cores)
     args = O.make_args(model_name=a.model, number_components=a.exemplars, training_set_size=a.train_size)
     p = O.init_params(args, seed=0)
     data = O.synthetic_dataset(a.train_size)
     gen = torch.Generator().manual_seed(1)
     st = {}
-    B = a.batch
 
     def one():
-        idx = torch.randint(0, a.train_size, (B,), generator=gen)
+        idx = torch.randint(0, a.train_size, (batch,), generator=gen)
         t0 = time.perf_counter()
         O.train_step(p, st, args, data[idx], idx.view(-1, 1), data, 1.0, gen)
         return time.perf_counter() - t0
@@ -118,8 +206,8 @@ def cpu_reference_run(a, steps, warmup, budget_s=240.0):
     k = max(1, min(steps, int(budget_s / max(warm[-1], 1e-3))))
     times = [one() for _ in range(k)]
     ms = 1e3 * sum(times) / len(times)
-    return {"value": B / (ms / 1e3), "ms_per_step": ms, "steps": k, "cores": cores,
-            "sample": f"{k} full steps of the same workload (B={B}, N={a.exemplars}, T={a.train_size}) after "
+    return {"value": batch / (ms / 1e3), "ms_per_step": ms, "steps": k, "cores": cores, "kind": "port",
+            "sample": f"{k} full steps of the same workload (B={batch}, N={a.exemplars}, T={a.train_size}) after "
                       f"{len(warm)} warm-up; oracle port (torch-CPU fp32, fp64 distance) with {cores} threads"}
 
 
@@ -127,27 +215,21 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(a, a.steps, min(max(a.warmup, 1), 3), budget_s=30.0)   # bounded: ~30 s of CPU work
+    # same config as the GPU arm at this N: the reference is single-device, so it steps the GLOBAL batch
+    batch = a.batch * a.gpus if a.scaling == "weak" else a.batch
+    w = min(max(a.warmup, 1), 2)
+    r = cpu_reference_run(a, batch, a.steps, w, budget_s=30.0)   # bounded: ~30 s of timed CPU work
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "imgs/s", "n_gpus": a.gpus,
-        "steps": r["steps"], "warmup": min(max(a.warmup, 1), 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, 1),
-        "cpu_baseline": {"value": r["value"], "unit": "imgs/s", "cores": r["cores"], "kind": "port",
+        "steps": r["steps"], "warmup": w, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, a.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": "imgs/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-
-
-def workload_config(a, world):
-    return {"workload": f"{a.model}+exemplar_prior, synthetic dynamic-MNIST 28x28 Bernoulli, T={a.train_size}, "
-                        f"N={a.exemplars} exemplars/step (exact prior, encoded with grad), D=40, hidden 300, "
-                        f"batch {a.batch}/GPU",
-            "global_batch": a.batch * world, "bank": "replicated" if world == 1 else "range-sharded over ranks",
-            "l2": "per-step working set (~0.5 GB activations + 78 MB exemplar gather) exceeds the 126 MB L2; no explicit flush",
-            "cuda_graph": not a.no_graph}
+    print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------- GPU
@@ -166,13 +248,125 @@ def _dbg(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+def dense_call_flops(name, args):
+    """Algorithmic GEMM flops of one dense-layer entry-point call, from its own arguments (include/exvae_b200.h)."""
+    if name == "exvae_gated_dense_fwd":
+        R, K, O = args[5:8]
+        return 2.0 * R * K * 2 * O, (R, K, 2 * O)
+    if name == "exvae_gated_dense_bwd":
+        R, K, O = args[6:9]
+        return 2.0 * R * K * 2 * O * (2 if args[9] else 1), (R, K, 2 * O)      # dW (+ dx when requested)
+    if name == "exvae_linear_fwd":
+        R, K, O = args[3:6]
+        return 2.0 * R * K * O, (R, K, O)
+    if name == "exvae_linear_bwd":
+        R, K, O = args[4:7]
+        return 2.0 * R * K * O * (2 if args[10] else 1), (R, K, O)
+    return None, None
+
+
+def sharded_parity(a, args, dataset, dev, world, rank):
+    """tests/manual/mgpu_check.py on the bench workload: ONE training step with the bank range-sharded over the
+    ranks (each rank its own B rows) must reproduce the single-GPU step over the concatenated batch.  Returns
+    {"loss_rel", "worst_grad_rel"} on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import exemplar_vae_b200 as E
+    from exemplar_vae_b200 import distributed as D
+    B = a.batch if a.scaling == "weak" else a.batch // world
+    T, N = a.train_size, a.exemplars
+    gen = torch.Generator().manual_seed(4321)                      # identical draws on every rank
+    bidx = torch.randperm(T, generator=gen)[:B * world]
+    x = torch.bernoulli(dataset.tensors[0][bidx], generator=gen)
+    ex_idx = torch.randint(0, T, (N,), generator=gen)
+    ex_idx[:8] = bidx[:8]
+    n_eps = 1 if a.model == "vae" else 2
+    eps = [torch.randn(B * world, 40, generator=gen) for _ in range(n_eps)]
+    torch.manual_seed(1)
+    ref = E.importing_model(args)(args).to(dev)
+    for p in ref.parameters():
+        dist.broadcast(p.data, src=0)
+    ref.train()
+    m = E.importing_model(args)(args).to(dev)
+    m.load_state_dict(ref.state_dict())
+    m.train()
+    D.shard_bank(m, None, dist.group.WORLD)
+    sl = slice(rank * B, (rank + 1) * B)
+    m.rng_override = {"eps": [e[sl].to(dev) for e in eps], "exemplar_indices": ex_idx.to(dev)}
+    loss, RE, KL = m.calculate_loss((x[sl].to(dev), bidx[sl].view(-1, 1).to(dev)), 0.7, average=True, dataset=dataset)
+    loss.backward()
+    m.grad_sync()
+    l3 = torch.stack((loss.detach(), RE.detach(), KL.detach()))
+    dist.all_reduce(l3)
+    l3 /= world
+    out = None
+    if rank == 0:
+        ref.rng_override = {"eps": [e.to(dev) for e in eps], "exemplar_indices": ex_idx.to(dev)}
+        l, r, k = ref.calculate_loss((x.to(dev), bidx.view(-1, 1).to(dev)), 0.7, average=True, dataset=dataset)
+        l.backward()
+        r3 = torch.stack((l.detach(), r.detach(), k.detach()))
+        worst = 0.0
+        for pa, pb in zip(m.parameters(), ref.parameters()):
+            scale = pb.grad.abs().max().item() + 1e-12
+            worst = max(worst, (pa.grad - pb.grad).abs().max().item() / scale)
+        out = {"loss_rel": float(((l3 - r3).abs() / r3.abs()).max()), "worst_grad_rel": worst,
+               "rows": B * world, "what": "1 step, bank sharded over the ranks vs the same step on one GPU over the "
+                                          "concatenated batch (loss/RE/KL, every parameter gradient / its max)"}
+    dist.barrier()
+    del m, ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def prior_bank_leg(a, dev, world, rank):
+    """cfg5: the N=100000 x D=128 exemplar bank, range-sharded over the ranks — K1 forward+backward for B=512 rows per
+    rank (all-gathered to world*B rows against the local shard) incl. the LSE-partial exchange."""
+    import torch
+    import torch.distributed as dist
+    from exemplar_vae_b200 import ops
+    B, N, D = 512, 100000, 128
+    C = N // world
+    g = torch.Generator().manual_seed(7 + rank)
+    mu = torch.randn(C, D, generator=g).to(dev).requires_grad_(True)
+    z = torch.randn(B, D, generator=g).to(dev).requires_grad_(True)
+    lv = torch.full((D,), -2.4189, device=dev, requires_grad=True)
+    zi = torch.randint(0, N, (B,), generator=g).to(dev)
+    mi = torch.randint(0, N, (C,), generator=g).to(dev)
+    grp = dist.group.WORLD if world > 1 else None
+
+    def one():
+        if world > 1:
+            lp = ops.prior_lse_sharded(z, mu, lv, zi, mi, N, grp)
+        else:
+            lp = ops.prior_lse(z, mu, lv, zi, mi)
+        lp.sum().backward()
+        z.grad = mu.grad = lv.grad = None
+
+    for _ in range(5):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 30
+    e0.record()
+    for _ in range(reps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"B_per_rank": B, "rows_per_call": B * world, "N": N, "N_per_rank": C, "D": D,
+            "fwd_bwd_ms": t.item(), "what": "prior_lse fwd + bwd (dz, dmu, dlogvar) incl. exchanges, eager, CUDA events, "
+                                            "max over ranks"}
+
+
 def run_gpu(a):
     import torch
     import torch.distributed as dist
     import exemplar_vae_b200 as E
     from exemplar_vae_b200 import ops
     from exemplar_vae_b200._lib import lib
-    from exemplar_vae_b200.config import default_args, synthetic_train_set
+    from exemplar_vae_b200.config import default_args
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,21 +375,36 @@ def run_gpu(a):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    if a.scaling == "strong":
+        assert a.batch % world == 0, "strong scaling splits the global batch evenly"
+    B = a.batch if a.scaling == "weak" else a.batch // world
+    N, T = a.exemplars, a.train_size
 
-    B, N, T = a.batch, a.exemplars, a.train_size
-    args = default_args(model_name=a.model, number_components=N, training_set_size=T, device="cuda", seed=rank)
+    args = default_args(device="cuda", seed=rank, **model_kwargs(a))
     torch.manual_seed(0)
     model = E.importing_model(args)(args).to(dev)
-    dataset = synthetic_train_set(T)                         # [T,784] U(0,1), CPU generator seed 1234
-    data_host = dataset.tensors[0]
+    data_host = synthetic_data(a)                            # [T,P] U(0,1), CPU generator seed 1234
+    dataset = torch.utils.data.TensorDataset(data_host, torch.arange(T).view(-1, 1), torch.zeros(T))
     opt = E.AdamNormGrad(model.parameters(), lr=5e-4)
+
+    parity = None
     if world > 1:
         from exemplar_vae_b200 import distributed as D
-        D.shard_bank(model, opt, dist.group.WORLD)
+        if not a.approximate and not a.no_parity and a.model in ("vae", "hvae_2level"):
+            parity = sharded_parity(a, args, dataset, dev, world, rank)
+            _dbg(f"sharded parity {parity}")
+        D.shard_bank(model, opt, dist.group.WORLD, shard=not a.approximate)
+    cache = None
+    if a.approximate:
+        with torch.no_grad():
+            cache = model.cache_z(dataset)                   # per-epoch cost in the reference (utils/training.py:20-23)
+        cache = (cache[0].contiguous(), cache[1].contiguous())
+    graphable = (not a.approximate) or getattr(model, "knn_graph_capturable", False)
+    use_graph = (not a.no_graph) and graphable
     _dbg("model built; capturing step")
-    step = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=3, use_graph=not a.no_graph)
+    step = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=3, use_graph=use_graph, cache=cache)
     _dbg("step ready")
 
     gen = torch.Generator().manual_seed(100 + rank)
@@ -250,24 +459,37 @@ def run_gpu(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world / (t.item() / 1e3)
     _dbg("e2e done")
-    h2d = B * CFG["P"] * 4 + B * 8
+    h2d = B * a.P * 4 + B * 8
     d2h = 3 * 4
 
     # ---- per-entry-point device time (eager, CUDA events on the launch stream) -------------
     # (every rank runs the same steps: they contain collectives; only rank 0 keeps the timings)
-    breakdown, prior_ms = {}, None
+    breakdown, calls = {}, {}
     L = lib()
-    eager = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=2, use_graph=False)
+    eager = E.GraphedTrainStep(model, opt, args, dataset, B, beta=1.0, warmup_steps=2, use_graph=False, cache=cache)
     L.profile = []
-    reps = 5
+    reps = 5 if not a.approximate else 2
     for k in range(reps):
         eager.step(dev_x[k % n_batches], dev_i[k % n_batches])
     torch.cuda.synchronize()
-    for name, s, e in L.profile:
-        breakdown[name] = breakdown.get(name, 0.0) + s.elapsed_time(e) / reps
+    gemm_ms = gemm_flops = 0.0
+    shapes = {}
+    for name, s, e, cargs in L.profile:
+        ms = s.elapsed_time(e) / reps
+        breakdown[name] = breakdown.get(name, 0.0) + ms
+        calls[name] = calls.get(name, 0) + 1
+        fl, shp = dense_call_flops(name, cargs)
+        if fl is not None:
+            gemm_ms += ms
+            gemm_flops += fl / reps
+            key = f"{name[6:]} R={shp[0]} K={shp[1]} O={shp[2]}"
+            ent = shapes.setdefault(key, [0.0, 0.0, 0])
+            ent[0] += ms; ent[1] += fl / reps; ent[2] += 1
     L.profile = None
     prior_ms = breakdown.get("exvae_prior_lse_fwd")
+    prior_calls = max(1, calls.get("exvae_prior_lse_fwd", reps) // reps)
     _dbg("profile done")
+    bank = prior_bank_leg(a, dev, world, rank) if a.config == "cfg5" else None
     if world > 1:
         dist.barrier()
 
@@ -276,72 +498,74 @@ def run_gpu(a):
         return
 
     hbm_peak, bf16_peak, peak_src = measured_peaks()
-    shard_N = N // world
-    alg_bytes = B * world * shard_N * CFG["D"] * 2          # north_star: B.N.D bf16 bytes per prior call (per GPU shard)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "prior_fwd_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = None
-    backend = ops.gemm_backend()
-    if prior_ms:
-        ach = alg_bytes / (prior_ms / 1e3) / 1e9
-        roofline = {"kernel": "exvae_prior_lse_fwd = prior_stage + prior_mask_list + prior_lse_fwd_tc_kernel "
-                              "(tcgen05 3xTF32, TMEM online LSE) + lse_merge",
-                    "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src, "ms_per_launch": prior_ms,
-                    "model": "algorithmic bytes = B*N*D*2 per call (north_star / SURVEY 8d streaming model, B and N per "
-                             "rank); measured DRAM traffic is ~10 MB (the staged hi/lo planes of the bank, read once) because tiles are reused from shared "
-                             "memory/L2, so frac > 1 is expected; the true limiter is the MUFU/ALU rate of the soft-max "
-                             "epilogue plus fixed launch/staging latency at this size"}
-    gemm_ms = sum(v for k, v in breakdown.items() if "dense" in k or "linear" in k)
-    flops = step_gemm_flops(a.model, B * world, shard_N, B)
     tf32_peak = bf16_peak / 2.0
-    ach_alg = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
-    extra = {
-        "roofline_gemm": {"kernel": "gemm_tf32x3_kernel (all dense-layer entry points, incl. operand staging)",
-                          "backend": backend, "bound": "tensor",
-                          "achieved": ach_alg, "unit": "TFLOP/s (algorithmic fp32 GEMM flops)",
-                          "issued_tf32_tflops": 3.0 * ach_alg if ach_alg else None,
-                          "peak": bf16_peak, "peak_tf32_est": tf32_peak,
-                          "frac": (3.0 * ach_alg / tf32_peak) if ach_alg else None,
-                          "note": "3xTF32 error compensation issues 3 tf32 MMAs per product (parity bar 1e-4 rules out "
-                                  "single-pass tf32/bf16); frac = issued tf32 flops / (measured bf16 peak / 2)",
-                          "ms_per_step": gemm_ms},
-        "breakdown_ms": {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
+    ach_alg = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
+    top = sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]
+    roofline = {
+        "kernel": "gemm_tf32x3_kernel — every dense-layer C-ABI call of one step (gated_dense/linear fwd+bwd, incl. their "
+                  "staging/finish kernels): the dominant kernel of the step",
+        "bound": "tensor",
+        "achieved": 3.0 * ach_alg if ach_alg else None,
+        "peak": tf32_peak, "unit": "TFLOP/s", "frac": (3.0 * ach_alg / tf32_peak) if ach_alg else None,
+        "traffic": None,
+        "algorithmic_tflops": ach_alg, "algorithmic_gflop_per_step": gemm_flops / 1e9, "ms_per_step": gemm_ms,
+        "peak_source": f"{peak_src}: dense bf16 {bf16_peak} TFLOP/s / 2 as the TF32 estimate",
+        "model": "achieved = ISSUED tf32 flops = 3 x algorithmic fp32 GEMM flops (error-compensated 3xTF32: the 1e-4 "
+                 "parity bar rules out single-pass tf32/bf16) / summed CUDA-event time of the dense entry points in an "
+                 "eager replay of the same step; flops counted from each call's own (R,K,O)",
+        "top_shapes": [{"call": k, "ms": round(v[0], 4), "issued_tflops": round(3 * v[1] / (v[0] / 1e3) / 1e12, 1)
+                        if v[0] > 0 else None, "calls": v[2] // reps} for k, v in top],
     }
-
+    roofline_prior = None
+    if prior_ms:
+        rows = B * world if (world > 1 and not a.approximate) else B
+        shard_N = (N // world) if (world > 1 and not a.approximate) else N
+        D = 40
+        per_call_ms = prior_ms / prior_calls
+        alg_bytes = rows * shard_N * D * 2          # north_star: B.N.D bf16 bytes per prior call (per GPU shard)
+        compulsory = (shard_N * D + rows * D) * 4 + shard_N * 8 + rows * 12
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "prior_fwd_traffic.json")
+        if os.path.exists(tp) and world == 1 and a.config == "cfg2" and not a.approximate:
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = "from profiles/prior_fwd_traffic.json (ncu --set full capture of this shape, 1 GPU)"
+        if not a.approximate:
+            ach = alg_bytes / (per_call_ms / 1e3) / 1e9
+            roofline_prior = {
+                "kernel": "exvae_prior_lse_fwd (K1 forward)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "traffic_note": traffic_note,
+                "physical": False, "ms_per_launch": per_call_ms,
+                "compulsory_bytes": compulsory, "compulsory_gbs": compulsory / (per_call_ms / 1e3) / 1e9,
+                "model": "BASELINE.json's contract figure: algorithmic bytes = B*N*D*2 per call (north_star / SURVEY 8d "
+                         "streaming model, B and N per rank).  NOT a physical roofline fraction: the tiled kernel reads "
+                         "the bank once (compulsory_bytes), so frac > 1; the kernel is MUFU/latency bound"}
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         try:
-            r = cpu_reference_run(a, steps=5, warmup=2, budget_s=30.0)
-            cpu = {"value": r["value"], "unit": "imgs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+            r = cpu_reference_run(a, B, steps=5, warmup=1, budget_s=25.0)
+            cpu = {"value": r["value"], "unit": "imgs/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                    "ms_per_step": r["ms_per_step"]}
         except Exception as ex:   # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": "imgs/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "imgs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(a, world),
         "e2e": {"value": e2e_value, "unit": "imgs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t.item()},
         "gpu_launches": step.launches_per_step * a.steps, "launches_per_step": step.launches_per_step,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "last_loss_re_kl": last,
+        "clocks": clocks, "roofline": roofline, "roofline_prior": roofline_prior, "cpu_baseline": cpu,
+        "last_loss_re_kl": last, "gemm_backend": ops.gemm_backend(), "cuda_graph": use_graph,
+        "breakdown_ms": {k: round(v, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
     }
-    line.update(extra)
+    if parity is not None:
+        line["parity_sharded"] = parity
+    if bank is not None:
+        line["prior_bank"] = bank
     print(json.dumps(line), flush=True)
     _finish(world)
-
-
-def step_gemm_flops(model, rows_batch, rows_bank, B):
-    """Algorithmic GEMM flops of one step on ONE rank (fwd + dW + dX where needed) for model=vae."""
-    P, H, D = CFG["P"], CFG["H"], CFG["D"]
-    enc = lambda R: 2.0 * R * (P * 2 * H + H * 2 * H + H * D)              # trunk + mean head
-    enc_bwd = lambda R: 2.0 * R * (P * 2 * H) + 2 * 2.0 * R * (H * 2 * H + H * D)   # first layer: dW only
-    dec = 2.0 * B * (D * 2 * H + H * 2 * H + H * P)
-    head = 2.0 * B * H * D                                                 # logvar head, batch rows only
-    return enc(rows_bank) + enc(B) + enc_bwd(rows_bank) + enc_bwd(B) + 3 * (dec + head)
 
 
 def main():

@@ -81,7 +81,7 @@ class _Lib:
             e0.record()
             rc = fn(*args)
             e1.record()
-            prof.append((name, e0, e1))
+            prof.append((name, e0, e1, args))
             return rc
         call.__name__ = name
         return call

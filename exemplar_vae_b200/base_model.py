@@ -16,6 +16,7 @@ B200-first differences that do not change results:
 from __future__ import annotations
 
 import math
+import weakref
 from abc import ABC, abstractmethod
 from typing import Optional
 
@@ -82,6 +83,7 @@ class BaseModel(nn.Module, ABC):
         self.fuse_exemplar_encoder = True           # encode batch + exemplars in ONE pass of the shared trunk
         self.overlap_prior = False                  # run the prior term on a side stream next to the decoder (AbsModel)
         self._z_event = None
+        self._emb_before_z = False                  # exemplar embedding was produced BEFORE z on the main stream
         self._side_streams = {}
         self._zero_rows = {}
         self._resident_cache = {}
@@ -123,12 +125,20 @@ class BaseModel(nn.Module, ABC):
         dev = self.prior_device()
         if src.is_cuda:
             return src
-        key = (src.data_ptr(), tuple(src.shape))
-        hit = self._resident_cache.get(key)
-        if hit is None:
-            hit = src.to(dev, dtype=torch.float32).contiguous()
-            self._resident_cache = {key: hit}
+        # keyed on the tensor OBJECT (weak reference) and its version counter: a new dataset tensor at a recycled
+        # address, or an in-place edit of the data (re-binarisation, swapped splits), uploads again
+        ent = self._resident_cache.get("entry")
+        if ent is not None:
+            ref, version, shape, hit = ent
+            if ref() is src and version == src._version and shape == tuple(src.shape):
+                return hit
+        hit = src.to(dev, dtype=torch.float32).contiguous()
+        self._resident_cache = {"entry": (weakref.ref(src), src._version, tuple(src.shape), hit)}
         return hit
+
+    def invalidate_resident(self):
+        """Drop the device copy of the train set (the next ``resident`` call uploads again)."""
+        self._resident_cache = {}
 
     def prior_device(self):
         return next(self.parameters()).device
@@ -148,11 +158,14 @@ class BaseModel(nn.Module, ABC):
         """models/BaseModel.py:65-77 — returns (loss, RE, KL): scalars if ``average`` else [B]."""
         x, x_indices = x
         zq = None
+        self._z_event = None             # never reuse a fork point recorded by an earlier forward()
+        self._emb_before_z = exemplars_embedding is not None
         if (self.fuse_exemplar_encoder and exemplars_embedding is None and dataset is not None
                 and self.args.prior == 'exemplar_prior' and self.args.approximate_prior is False):
             # B200-first: the reference encodes the batch (q_z(x)) and the N exemplars (q_z(.., prior=True))
             # in two passes of the same trunk; here they share one GEMM chain over B+N rows.
             zq, exemplars_embedding = self.q_z_with_exemplars(x, dataset)
+            self._emb_before_z = True
         x_mean, x_logvar, latent_stats = self.forward(x, zq=zq)
         RE = self.reconstruction_loss(x.reshape(x_mean.shape), x_mean, x_logvar)
         KL = self.kl_loss(latent_stats, exemplars_embedding, dataset, cache, x_indices)
@@ -203,6 +216,42 @@ class BaseModel(nn.Module, ABC):
         masked = (test is False) and (self.args.no_mask is False)
         return ops.prior_logprob_matrix(z, centers, lv, z_indices if masked else None,
                                         center_indices if masked else None)
+
+    def _log_p_z_branch(self, z_q, x_indices, exemplars_embedding):
+        """log p(z) of the exemplar prior, on a side stream next to the decoder when ``overlap_prior`` recorded a
+        fork point in forward()."""
+        ev, self._z_event = self._z_event, None
+        if (ev is not None and self._emb_before_z and self.args.prior == 'exemplar_prior'
+                and isinstance(exemplars_embedding, tuple)):
+            # The prior term and the decoder are independent chains between z and the loss, and the decoder's
+            # GEMMs over B rows leave most SMs idle: run K1 on a side stream forked at the point where z became
+            # available.  Only when the exemplar embedding was enqueued BEFORE that point on the main stream (the
+            # fused batch+exemplar encoder pass, or a bank handed in by the caller): an embedding built afterwards
+            # (get_exemplar_set above) is not ordered before the fork event.  Autograd replays the same fork in the
+            # backward (each node runs on its forward stream), and a capturing stream turns it into two parallel
+            # graph branches.  With a range-sharded bank the branch also carries the LSE-partial exchange.
+            cur = torch.cuda.current_stream()
+            side = self._prior_stream()
+            centers, clv, cidx = exemplars_embedding
+            emb = (centers, self._bank_logvar_row(clv), cidx)     # the parameter's view is taken on this stream
+            c_total = getattr(exemplars_embedding, "c_total", None)
+            if c_total is not None:
+                from .distributed import ShardedBank
+                emb = ShardedBank(emb, c_total)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=emb)
+            cur.wait_stream(side)
+            log_p_z.record_stream(cur)
+            return log_p_z
+        return self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+
+    def _prior_stream(self):
+        dev = torch.cuda.current_device()
+        st = self._side_streams.get(dev)
+        if st is None:
+            st = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+        return st
 
     # ------------------------------------------------------------------ VampPrior
     def add_pseudoinputs(self):
@@ -405,34 +454,9 @@ class AbsModel(BaseModel):
         z_q, z_q_mean, z_q_logvar = latent_stats
         if exemplars_embedding is None and self.args.prior == 'exemplar_prior':
             exemplars_embedding = self.get_exemplar_set(z_q_mean, z_q_logvar, dataset, cache, x_indices)
-        ev, self._z_event = self._z_event, None
-        if (ev is not None and self.args.prior == 'exemplar_prior' and self.bank_group is None
-                and isinstance(exemplars_embedding, tuple)):
-            # The prior term and the decoder are independent chains between z and the loss, and the decoder's
-            # GEMMs over B rows leave most SMs idle: run K1 on a side stream forked at the point where z (and the
-            # exemplar embeddings, computed before it) became available.  Autograd replays the same fork in the
-            # backward (each node runs on its forward stream), and a capturing stream turns it into two
-            # parallel graph branches.
-            cur = torch.cuda.current_stream()
-            side = self._prior_stream()
-            centers, clv, cidx = exemplars_embedding
-            emb = (centers, self._bank_logvar_row(clv), cidx)     # the parameter's view is taken on this stream
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=emb)
-            cur.wait_stream(side)
-            log_p_z.record_stream(cur)
-        else:
-            log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+        log_p_z = self._log_p_z_branch(z_q, x_indices, exemplars_embedding)
         log_q_z = log_normal_diag(z_q, z_q_mean, z_q_logvar, dim=1)
         return ops.lincomb((-1.0, 1.0), log_p_z, log_q_z)     # -(log_p_z - log_q_z)
-
-    def _prior_stream(self):
-        dev = torch.cuda.current_device()
-        st = self._side_streams.get(dev)
-        if st is None:
-            st = self._side_streams[dev] = torch.cuda.Stream(device=dev)
-        return st
 
     def generate_x_from_z(self, z, with_reparameterize=True):
         generated_x, _ = self.p_x(z)
@@ -484,7 +508,7 @@ class BaseHModel(BaseModel):
         D1, D2 = self.args.z1_size, self.args.z2_size
         log_p_z1 = log_normal_diag(z1_q.view(-1, D1), z1_p_mean.view(-1, D1), z1_p_logvar.view(-1, D1), dim=1)
         log_q_z1 = log_normal_diag(z1_q.view(-1, D1), z1_q_mean.view(-1, D1), z1_q_logvar.view(-1, D1), dim=1)
-        log_p_z2 = self.log_p_z(z=(z2_q, x_indices), exemplars_embedding=exemplars_embedding)
+        log_p_z2 = self._log_p_z_branch(z2_q, x_indices, exemplars_embedding)
         log_q_z2 = log_normal_diag(z2_q.view(-1, D2), z2_q_mean.view(-1, D2), z2_q_logvar.view(-1, D2), dim=1)
         return ops.lincomb((-1.0, -1.0, 1.0, 1.0), log_p_z1, log_p_z2, log_q_z1, log_q_z2)
 
@@ -533,6 +557,8 @@ class BaseHModel(BaseModel):
     def forward(self, x, zq=None):
         z2_q_mean, z2_q_logvar = self.q_z(x) if zq is None else zq
         z2_q = self.reparameterize(z2_q_mean, z2_q_logvar, sub=0)
+        if self.overlap_prior and z2_q.is_cuda:
+            self._z_event = torch.cuda.current_stream().record_event()   # fork point of the prior branch (kl_loss)
         z1_q_mean, z1_q_logvar = self.q_z1(x, z2_q)
         z1_q = self.reparameterize(z1_q_mean, z1_q_logvar, sub=1)
         z1_p_mean, z1_p_logvar = self.p_z1(z2_q)

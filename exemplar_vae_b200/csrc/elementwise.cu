@@ -149,9 +149,11 @@ __global__ void __launch_bounds__(256) logistic_bwd_kernel(const float* __restri
 
 // out3 = {mean(-RE + beta*KL), mean(RE), mean(KL)} or per-sample loss
 __global__ void __launch_bounds__(1024) elbo_reduce_kernel(const float* __restrict__ RE, const float* __restrict__ KL,
-                                                           int B, float beta, int average, float* __restrict__ out3,
+                                                           int B, float beta, const float* __restrict__ beta_dev,
+                                                           int average, float* __restrict__ out3,
                                                            float* __restrict__ loss_b) {
   __shared__ float sh[3][32];
+  if (beta_dev) beta = *beta_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float a = 0.f, r = 0.f, k = 0.f;
   for (int b = tid; b < B; b += blockDim.x) {
@@ -195,10 +197,11 @@ __global__ void __launch_bounds__(256) lincomb4_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) elbo_reduce_bwd_kernel(const float* __restrict__ g3,
                                                               const float* __restrict__ g_loss_b, int B, float beta,
-                                                              int average, float* __restrict__ dRE,
-                                                              float* __restrict__ dKL) {
+                                                              const float* __restrict__ beta_dev, int average,
+                                                              float* __restrict__ dRE, float* __restrict__ dKL) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (beta_dev) beta = *beta_dev;
   if (average) {
     const float inv = 1.f / (float)B;
     dRE[b] = (-g3[0] + g3[1]) * inv;
@@ -449,11 +452,11 @@ extern "C" int exvae_log_logistic256_bwd(const float* x, const float* mean, cons
   const long long n = (long long)B * P;
   EW_LAUNCH(logistic_bwd_kernel, n, x, mean, logvar, dout, n, P, dmean, dlogvar);
 }
-extern "C" int exvae_elbo_reduce(const float* RE, const float* KL, int B, float beta, int average, float* out3,
-                                 float* loss_b, exvae_stream_t stream) {
+extern "C" int exvae_elbo_reduce(const float* RE, const float* KL, int B, float beta, const float* beta_dev, int average,
+                                 float* out3, float* loss_b, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(RE && KL && B > 0);
   EXVAE_CHECK_ARG(average ? out3 != nullptr : loss_b != nullptr);
-  elbo_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(RE, KL, B, beta, average, out3, loss_b);
+  elbo_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(RE, KL, B, beta, beta_dev, average, out3, loss_b);
   EXVAE_RETURN_LAST_ERROR();
 }
 
@@ -463,11 +466,11 @@ extern "C" int exvae_lincomb4(const float* x0, const float* x1, const float* x2,
   EW_LAUNCH(lincomb4_kernel, n, x0, x1, x2, x3, c0, c1, c2, c3, n, out);
 }
 
-extern "C" int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int B, float beta, int average,
-                                     float* dRE, float* dKL, exvae_stream_t stream) {
+extern "C" int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int B, float beta, const float* beta_dev,
+                                     int average, float* dRE, float* dKL, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(dRE && dKL && B > 0);
   EXVAE_CHECK_ARG(average ? g3 != nullptr : g_loss_b != nullptr);
-  elbo_reduce_bwd_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(g3, g_loss_b, B, beta, average, dRE, dKL);
+  elbo_reduce_bwd_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(g3, g_loss_b, B, beta, beta_dev, average, dRE, dKL);
   EXVAE_RETURN_LAST_ERROR();
 }
 

@@ -54,11 +54,14 @@ class FlatGrads:
         self.buf.mul_(1.0 / world)
 
 
-def shard_bank(model, optimizer=None, group=None):
-    """Switch ``model`` to a range-sharded exemplar bank + data-parallel gradients over ``group``."""
+def shard_bank(model, optimizer=None, group=None, shard=True):
+    """Switch ``model`` to a range-sharded exemplar bank + data-parallel gradients over ``group``.
+    ``shard=False`` keeps the bank replicated (pure data parallelism: every rank draws all N exemplars /
+    runs the kNN selection against its own cache) and only averages the gradients."""
     group = group if group is not None else dist.group.WORLD
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    model.bank_group, model.bank_world, model.bank_rank = group, world, rank
+    if shard:
+        model.bank_group, model.bank_world, model.bank_rank = group, world, rank
     # decorrelate the per-rank draws (exemplar indices, eps, binarisation)
     model.rng.seed = (model.rng.seed * 1000003 + 7919 * (rank + 1)) & 0xFFFFFFFFFFFFFFFF
     # identical initial weights on every rank

@@ -146,9 +146,11 @@ class WNConv2d(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True):
         super().__init__()
         ref = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
-        self.weight_v = nn.Parameter(ref.weight.detach().clone())
-        self.weight_g = nn.Parameter(ref.weight.detach().flatten(1).norm(dim=1).view(-1, 1, 1, 1).clone())
+        # registration order = torch.nn.utils.weight_norm(nn.Conv2d): bias, weight_g, weight_v.  Optimizer state is
+        # positional, so a reference checkpoint's Adam moments only line up with this order.
         self.bias = nn.Parameter(ref.bias.detach().clone()) if bias else None
+        self.weight_g = nn.Parameter(ref.weight.detach().flatten(1).norm(dim=1).view(-1, 1, 1, 1).clone())
+        self.weight_v = nn.Parameter(ref.weight.detach().clone())
         self._stride, self._pad = _pair(stride)[0], _pair(padding)[0]
 
     def weight(self):

@@ -450,11 +450,14 @@ def _grad_sink(*params):
 _FUSE_GRAD_ACCUM = False
 
 
-def set_fused_grad_accumulation(on: bool) -> None:
+def set_fused_grad_accumulation(on: bool) -> bool:
     """When on, dense layers ADD their weight/bias gradients directly into existing ``.grad`` buffers
-    inside the backward kernels (autograd then sees no gradient for those parameters)."""
+    inside the backward kernels (autograd then sees no gradient for those parameters).  Returns the
+    previous setting so callers can scope it."""
     global _FUSE_GRAD_ACCUM
+    prev = _FUSE_GRAD_ACCUM
     _FUSE_GRAD_ACCUM = bool(on)
+    return prev
 
 
 def gated_dense(x, Wh, bh, Wg, bg) -> torch.Tensor:
@@ -666,14 +669,23 @@ class _ElboReduce(torch.autograd.Function):
         L = lib()
         RE, KL = _f32(RE), _f32(KL)
         B = RE.numel()
-        ctx.cfg = (B, float(beta), bool(average))
+        # beta is a host float, or a [1] fp32 device tensor the kernels read at run time (a captured graph then
+        # follows the warm-up schedule of utils/training.py:5-12 without being rebuilt)
+        beta_dev = beta if torch.is_tensor(beta) else None
+        if beta_dev is not None:
+            assert beta_dev.is_cuda and beta_dev.dtype == torch.float32 and beta_dev.numel() == 1
+        beta_f = 0.0 if beta_dev is not None else float(beta)
+        ctx.cfg = (B, beta_f, bool(average))
+        ctx.beta_dev = beta_dev
         if average:
             out3 = torch.empty((3,), dtype=torch.float32, device=RE.device)
-            L.check(L.exvae_elbo_reduce(_p(RE), _p(KL), B, beta, 1, _p(out3), None, _stream()), "elbo_reduce")
+            L.check(L.exvae_elbo_reduce(_p(RE), _p(KL), B, beta_f, _p(beta_dev), 1, _p(out3), None, _stream()),
+                    "elbo_reduce")
             _count(1)
             return out3
         loss_b = torch.empty((B,), dtype=torch.float32, device=RE.device)
-        L.check(L.exvae_elbo_reduce(_p(RE), _p(KL), B, beta, 0, None, _p(loss_b), _stream()), "elbo_reduce")
+        L.check(L.exvae_elbo_reduce(_p(RE), _p(KL), B, beta_f, _p(beta_dev), 0, None, _p(loss_b), _stream()),
+                "elbo_reduce")
         _count(1)
         return loss_b
 
@@ -685,15 +697,16 @@ class _ElboReduce(torch.autograd.Function):
         dRE = torch.empty((B,), dtype=torch.float32, device=g.device)
         dKL = torch.empty((B,), dtype=torch.float32, device=g.device)
         L.check(L.exvae_elbo_reduce_bwd(_p(g) if average else None, None if average else _p(g), B, beta,
-                                        1 if average else 0, _p(dRE), _p(dKL), _stream()), "elbo_reduce_bwd")
+                                        _p(ctx.beta_dev), 1 if average else 0, _p(dRE), _p(dKL), _stream()),
+                "elbo_reduce_bwd")
         _count(1)
         return dRE, dKL, None, None
 
 
-def elbo_reduce(RE, KL, beta: float, average: bool):
+def elbo_reduce(RE, KL, beta, average: bool):
     """models/BaseModel.py:71-75.  average=True -> tensor [3] = (mean loss, mean RE, mean KL);
-    average=False -> per-sample loss [B]."""
-    return _ElboReduce.apply(RE, KL, float(beta), bool(average))
+    average=False -> per-sample loss [B].  ``beta``: float or [1] fp32 device tensor."""
+    return _ElboReduce.apply(RE, KL, beta if torch.is_tensor(beta) else float(beta), bool(average))
 
 
 # ======================================================================================

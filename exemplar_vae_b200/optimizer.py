@@ -25,6 +25,10 @@ class AdamNormGrad(Optimizer):
                 st['step'] = 0
                 st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            if st['exp_avg'].shape != p.shape or st['exp_avg_sq'].shape != p.shape:
+                raise RuntimeError(
+                    f"AdamNormGrad: optimizer state of shape {tuple(st['exp_avg'].shape)} does not match its parameter "
+                    f"of shape {tuple(p.shape)} (state_dict loaded with a different parameter order?)")
             g = p.grad
             rows.append((p.data_ptr(), g.data_ptr() if g is not None else 0, st['exp_avg'].data_ptr(),
                          st['exp_avg_sq'].data_ptr(), p.numel()))
@@ -40,12 +44,18 @@ class AdamNormGrad(Optimizer):
                 'table': torch.tensor(rows, dtype=torch.int64).to(dev),
                 'norms': torch.empty(16 * len(rows) + 4, dtype=torch.float32, device=dev),   # 16 partials per tensor + step size
                 'step': (ent['step'] if ent is not None else
-                         torch.full((1,), int(self.state[group['params'][0]].get('step', 0)), dtype=torch.int64,
-                                    device=dev)),
+                         torch.full((1,), self.initial_step(gi), dtype=torch.int64, device=dev)),
                 'max_numel': max(r[4] for r in rows),
             }
             self._tables[gi] = ent
         return ent
+
+    def initial_step(self, gi: int) -> int:
+        """Step count a fresh device counter of group ``gi`` starts from: the largest per-parameter ``step`` of the
+        (possibly just loaded) state.  The reference keeps one count per parameter (utils/optimizer.py:60); they are
+        all equal whenever every parameter receives a gradient each step, which holds for the in-scope models."""
+        steps = [int(self.state[p].get('step', 0)) for p in self.param_groups[gi]['params'] if len(self.state[p])]
+        return max(steps) if steps else 0
 
     def zero_grad(self, set_to_none: bool = False):
         """Keeps gradient buffers in place (stable pointers for the fused step and for CUDA graphs)."""

@@ -52,23 +52,34 @@ class GraphedTrainStep:
     """One training step (dynamic binarisation, loss, backward, AdamNormGrad) captured ONCE in a
     CUDA graph and replayed: the launch-bound inner loop of utils/training.py:27-46 without any
     per-step Python or host sync.  Inputs are copied into static device buffers (``data`` [B,P]
-    fp32 probabilities, ``indices`` [B,1] int64); ``out`` holds (loss, RE, KL) of the last step."""
+    fp32 probabilities, ``indices`` [B,1] int64); ``out`` holds (loss, RE, KL) of the last step.
 
-    def __init__(self, model, optimizer, args, dataset, batch_size, beta=1.0, warmup_steps=3, use_graph=True):
-        self.model, self.opt, self.args, self.dataset, self.beta = model, optimizer, args, dataset, beta
+    Constructing the object does NOT train: the eager warm-up steps that settle the allocator, the
+    optimizer state and the gradient buffers run on the (all-zero) static buffers, and parameters,
+    Adam moments, the step counters and the RNG counter are restored afterwards.  ``beta`` lives in a
+    device scalar (``set_beta``), so one captured graph follows the warm-up schedule of
+    utils/training.py:5-12.  ``rng_override`` = {"eps": [static tensors], "exemplar_indices": static
+    tensor} injects the random draws (tests): overwrite those tensors in place between steps."""
+
+    def __init__(self, model, optimizer, args, dataset, batch_size, beta=1.0, warmup_steps=3, use_graph=True,
+                 rng_override=None, cache=None):
+        self.model, self.opt, self.args, self.dataset = model, optimizer, args, dataset
         dev = next(model.parameters()).device
         P = model.resident(dataset).shape[1]
         self.data = torch.zeros(batch_size, P, dtype=torch.float32, device=dev)
         self.indices = torch.zeros(batch_size, 1, dtype=torch.int64, device=dev)
         self.out = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.beta_dev = torch.full((1,), float(beta), dtype=torch.float32, device=dev)
+        self.rng_override = rng_override
+        self.cache = cache
         self.graph = None
         self.launches_per_step = 0
         if getattr(model, "flat_grads", None) is None:
             from .distributed import FlatGrads
             model.flat_grads = FlatGrads(model.parameters())     # stable grad pointers, one memset per step
-        ops.set_fused_grad_accumulation(True)                    # dW/db are added into the flat buffer in-kernel
-        model.overlap_prior = getattr(model, "bank_group", None) is None   # prior || decoder as parallel graph branches
+        model.overlap_prior = True                               # prior || decoder as parallel graph branches
         model.train()
+        saved = self._snapshot()
         # eager warm-up on a side stream (allocator + optimizer state + grad buffers settle)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -79,19 +90,75 @@ class GraphedTrainStep:
                 self.launches_per_step = ops.launch_count() - n0
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._restore(saved)
         if use_graph:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._body()
+        torch.cuda.synchronize()
+
+    # -------------------------------------------------------------- state kept across the warm-up
+    def _snapshot(self):
+        dev = self.data.device
+        params = [p.detach().clone() for p in self.model.parameters()]
+        opt_state = {}
+        for group in self.opt.param_groups:
+            for p in group['params']:
+                st = self.opt.state.get(p)
+                if st:
+                    opt_state[p] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        counters = {gi: ent['step'].clone() for gi, ent in getattr(self.opt, "_tables", {}).items()}
+        cache = None if self.cache is None else tuple(c.detach().clone() for c in self.cache)
+        return params, opt_state, counters, self.model.rng.counter(dev).clone(), cache
+
+    @torch.no_grad()
+    def _restore(self, saved):
+        params, opt_state, counters, rng_counter, cache = saved
+        for p, v in zip(self.model.parameters(), params):
+            p.copy_(v)
+        for group in self.opt.param_groups:
+            for p in group['params']:
+                st = self.opt.state.get(p)
+                if not st:
+                    continue
+                old = opt_state.get(p)
+                for k, v in st.items():           # in place: the fused step's pointer table stays valid
+                    if torch.is_tensor(v):
+                        v.copy_(old[k]) if old is not None else v.zero_()
+                    else:
+                        st[k] = old[k] if old is not None else 0
+        for gi, ent in getattr(self.opt, "_tables", {}).items():
+            if gi in counters:
+                ent['step'].copy_(counters[gi])
+            else:
+                ent['step'].fill_(self.opt.initial_step(gi))     # from the restored per-parameter steps
+        self.model.rng.counter(self.data.device).copy_(rng_counter)
+        if cache is not None:
+            for c, v in zip(self.cache, cache):
+                c.copy_(v)
+        self.model.flat_grads.zero_()
+        self.out.zero_()
+
+    def set_beta(self, beta: float):
+        """New KL weight for the following steps (no re-capture: the kernels read the device scalar)."""
+        self.beta_dev.fill_(float(beta))
 
     def _body(self):
-        x = self.model.rng.bernoulli(self.data) if self.args.dynamic_binarization else self.data
-        self.model.flat_grads.zero_()
-        loss, RE, KL = self.model.calculate_loss((x, self.indices), self.beta, average=True, cache=None,
-                                                 dataset=self.dataset)
-        loss.backward()
-        if self.model.grad_sync is not None:
-            self.model.grad_sync()                 # data-parallel: one all-reduce of the flat gradient buffer
+        model = self.model
+        x = model.rng.bernoulli(self.data) if self.args.dynamic_binarization else self.data
+        model.flat_grads.zero_()
+        ro = self.rng_override
+        if ro is not None:
+            model.rng_override = {"eps": list(ro.get("eps", [])), "exemplar_indices": ro.get("exemplar_indices")}
+        prev = ops.set_fused_grad_accumulation(True)             # dW/db are added into the flat buffer in-kernel
+        try:
+            loss, RE, KL = model.calculate_loss((x, self.indices), self.beta_dev, average=True, cache=self.cache,
+                                                dataset=self.dataset)
+            loss.backward()
+        finally:
+            ops.set_fused_grad_accumulation(prev)
+        if model.grad_sync is not None:
+            model.grad_sync()                      # data-parallel: all-reduce of the flat gradient buffer
         self.opt.step()
         with torch.no_grad():
             base = loss._base            # calculate_loss(average=True) returns three views of one [3] tensor

@@ -213,9 +213,10 @@ EXVAE_API int exvae_log_logistic256_fwd(const float* x, const float* mean, const
 EXVAE_API int exvae_log_logistic256_bwd(const float* x, const float* mean, const float* logvar, const float* dout, int B, int P,
                               float* dmean, float* dlogvar, exvae_stream_t stream);
 /* loss = mean(-RE + beta*KL), RE.mean, KL.mean (models/BaseModel.py:71-75); out3 = {loss, RE, KL};
- * average=0 writes per-sample loss into loss_b [B] instead (out3 may be NULL). */
-EXVAE_API int exvae_elbo_reduce(const float* RE, const float* KL, int B, float beta, int average, float* out3, float* loss_b,
-                      exvae_stream_t stream);
+ * average=0 writes per-sample loss into loss_b [B] instead (out3 may be NULL).  beta_dev (nullable): a device
+ * scalar that overrides `beta`, so a captured CUDA graph follows the warm-up schedule of utils/training.py:5-12. */
+EXVAE_API int exvae_elbo_reduce(const float* RE, const float* KL, int B, float beta, const float* beta_dev, int average,
+                                float* out3, float* loss_b, exvae_stream_t stream);
 
 /* out[i] = sum_j c[j] * x_j[i] over up to 4 vectors (NULL x_j are skipped): the KL assembly
  * -(log_p_z1 + log_p_z2 - log_q_z1 - log_q_z2) of models/AbsModel.py:19, models/AbsHModel.py:29. */
@@ -223,8 +224,8 @@ EXVAE_API int exvae_lincomb4(const float* x0, const float* x1, const float* x2, 
                              float c2, float c3, int64_t n, float* out, exvae_stream_t stream);
 /* backward of exvae_elbo_reduce: g3 = upstream grads of {loss, RE, KL} (average=1) or g_loss_b [B]
  * (average=0, g3 ignored); writes dRE [B], dKL [B]. */
-EXVAE_API int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int B, float beta, int average, float* dRE,
-                                    float* dKL, exvae_stream_t stream);
+EXVAE_API int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int B, float beta, const float* beta_dev,
+                                    int average, float* dRE, float* dKL, exvae_stream_t stream);
 
 /* ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
  * Device-side replacements for torch.bernoulli (utils/training.py:31), torch.randint

@@ -171,7 +171,9 @@ def test_training_steps_track_oracle(model_name, B, N, T, H):
         assert np.mean(np.abs(a - b) > 2e-5) < 2e-3, k             # and all but near-zero-gradient elements agree
 
 
-def test_graphed_step_matches_eager_and_device_rng_runs():
+def test_graphed_step_device_rng_and_train_one_epoch_run():
+    """Smoke of the device-RNG replay path and the train_one_epoch API (the graph-vs-eager-vs-oracle parity of
+    the benchmarked path lives in tests/test_gpu_bench_path.py)."""
     import exemplar_vae_b200 as E
     T, B, N = 4000, 128, 1000
     args = O.make_args(model_name="vae", hidden_size=300, number_components=N, training_set_size=T, device="cuda")
