@@ -49,6 +49,7 @@ struct BwdP {
   const float* zs; const float* ms; const float* isig;
   int Bpad, Cpad, KP, NG, LD, B, C, D, ny, nsplit;
   float* dzs_part; float* rowsum_part; float* dmu; float* coldot_part;
+  float* gcol_part; float* tot_part;
   unsigned long long* trace;   // debug (exvae_gemm_set_trace): 8 words per CTA, null in production
 };
 
@@ -90,10 +91,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   };
   if (tid == 0) stamp(0);
   // TR = false: X = block blockIdx.y of 128 latents, Y = bank tiles [y0, y1) of split blockIdx.x (of nsplit)
-  // TR = true : X = bank tile blockIdx.x,            Y = all row blocks
+  // TR = true : X = bank tile blockIdx.x,            Y = row blocks [y0, y1) of split blockIdx.y (of gridDim.y: a
+  //             range-sharded bank has few exemplar tiles per rank, so the row blocks are split over CTAs as well
+  //             and prior_bwd_cols_kernel adds the partials in a fixed order)
   const int xi = TR ? blockIdx.x : blockIdx.y;
-  const int y0 = TR ? 0 : (int)(((long long)p.ny * blockIdx.x) / p.nsplit);
-  const int y1 = TR ? p.ny : (int)(((long long)p.ny * (blockIdx.x + 1)) / p.nsplit);
+  const int y0 = TR ? (int)(((long long)p.ny * blockIdx.y) / gridDim.y) : (int)(((long long)p.ny * blockIdx.x) / p.nsplit);
+  const int y1 = TR ? (int)(((long long)p.ny * (blockIdx.y + 1)) / gridDim.y)
+                    : (int)(((long long)p.ny * (blockIdx.x + 1)) / p.nsplit);
   const int nkb = (p.KP + 31) / 32;
   const int nks = p.KP / 8;
 
@@ -260,6 +264,17 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       for (int j = 0; j < 32; ++j)
         if (dbase + j < p.LD) dst[dbase + j] = (dbase + j < p.D) ? __uint_as_float(gv[j]) : 0.f;
       if (half == 0) p.rowsum_part[(size_t)blockIdx.x * p.Bpad + xrow] = tot;
+    } else if (gridDim.y > 1) {
+      // row blocks split over CTAs: emit this split's share of W^T.zs and of the column sums
+      float* dst = p.gcol_part + ((size_t)blockIdx.y * p.Cpad + xrow) * p.NG + dbase;
+      if (dbase < p.NG) {
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4)
+          if (dbase + j4 < p.NG)
+            *reinterpret_cast<float4*>(dst + j4) = make_float4(__uint_as_float(gv[j4]), __uint_as_float(gv[j4 + 1]),
+                                                               __uint_as_float(gv[j4 + 2]), __uint_as_float(gv[j4 + 3]));
+      }
+      if (half == 0) p.tot_part[(size_t)blockIdx.y * p.Cpad + xrow] = tot;
     } else {
       // dmu[n,d] = (G[n,d] - colsum_n ms[n,d]) / sigma_d ;  coldot[d] = sum_n (G[n,d] - colsum_n ms[n,d]) ms[n,d]
       // (per-thread work first, all loads up front; the column dots go through a [128][65] shared-memory patch in the
@@ -337,7 +352,43 @@ __global__ void __launch_bounds__(256) prior_bwd_prep_kernel(const float* __rest
   }
 }
 
+// finish of a row-split pass 2: one CTA (128 threads = exemplar rows) per tile adds the splits in a fixed order,
+//   dmu[n,d] = (G[n,d] - colsum_n ms[n,d]) / sigma_d ;  coldot_part[tile][d] = sum_n (G[n,d] - colsum_n ms[n,d]) ms[n,d]
+__global__ void __launch_bounds__(128) prior_bwd_cols_kernel(const float* __restrict__ gcol_part,
+                                                             const float* __restrict__ tot_part,
+                                                             const float* __restrict__ ms,
+                                                             const float* __restrict__ isig, int rsplit, int C, int D,
+                                                             int LD, int NG, int Cpad, float* __restrict__ dmu,
+                                                             float* __restrict__ coldot_part) {
+  __shared__ float red[4][132];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x * 128 + tid;
+  float tot = 0.f;
+  for (int s = 0; s < rsplit; ++s) tot += tot_part[(size_t)s * Cpad + n];
+  for (int d = 0; d < LD; ++d) {
+    float pd = 0.f;
+    if (d < D) {
+      float g = 0.f;
+      for (int s = 0; s < rsplit; ++s) g += gcol_part[((size_t)s * Cpad + n) * NG + d];
+      const float mv = ms[(size_t)n * LD + d];
+      const float dv = g - tot * mv;
+      if (n < C) dmu[(size_t)n * D + d] = dv * isig[d];
+      pd = dv * mv;
+    }
+    pd = warp_sum(pd);
+    if (lane == 0) red[warp][d] = pd;
+  }
+  __syncthreads();
+  for (int d = tid; d < LD; d += 128)
+    coldot_part[(size_t)blockIdx.x * LD + d] = d < D ? (red[0][d] + red[1][d]) + (red[2][d] + red[3][d]) : 0.f;
+}
+
 }  // namespace
+
+int prior_bwd_pass2_splits(int Bpad, int Cpad) {
+  const int ntile = Cpad / 128, rbs = Bpad / 128;
+  return std::max(1, std::min(rbs, sm_count() / std::max(ntile, 1)));
+}
 
 int prior_bwd_prep_launch(const float* zs, const float* ms, const float* g, const float* lse2, const int64_t* z_idx,
                           int B, int C, int D, int LD, int Bpad, int Cpad, int NG, float* zsT, float* msT, float* glp,
@@ -370,6 +421,7 @@ int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out
   p.glp = a.glp; p.lsp = a.lsp; p.zip = a.zip; p.cidx = a.cidx; p.zs = a.zs; p.ms = a.ms; p.isig = a.isig;
   p.Bpad = a.Bpad; p.Cpad = a.Cpad; p.KP = a.KP; p.NG = a.NG; p.LD = a.LD; p.B = a.B; p.C = a.C; p.D = a.D;
   p.dzs_part = a.dzs_part; p.rowsum_part = a.rowsum_part; p.dmu = a.dmu; p.coldot_part = a.coldot_part;
+  p.gcol_part = a.gcol_part; p.tot_part = a.tot_part;
   auto launch = [&](auto kern, dim3 grid, const CUtensorMap& x, const CUtensorMap& yk, const CUtensorMap& yt) -> int {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     kern<<<grid, BT_THREADS, SMEM, st>>>(x, yk, yt, p);
@@ -385,8 +437,15 @@ int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out
   // pass 2: lanes = exemplars of one tile, columns = all row blocks -> dmu, coldot
   p.ny = rbs; p.nsplit = 1;
   p.trace = tc_take_trace(8 * 400);
-  return a.zip ? launch(prior_bwd_tc_kernel<true, true>, dim3(ntile), mm, mz, mzt)
-               : launch(prior_bwd_tc_kernel<true, false>, dim3(ntile), mm, mz, mzt);
+  const int rsplit = (a.gcol_part && a.tot_part) ? prior_bwd_pass2_splits(a.Bpad, a.Cpad) : 1;
+  rc = a.zip ? launch(prior_bwd_tc_kernel<true, true>, dim3(ntile, rsplit), mm, mz, mzt)
+             : launch(prior_bwd_tc_kernel<true, false>, dim3(ntile, rsplit), mm, mz, mzt);
+  if (rc || rsplit == 1) return rc;
+  if (a.LD > 132) return EXVAE_ERR_UNSUPPORTED;
+  prior_bwd_cols_kernel<<<ntile, 128, 0, st>>>(a.gcol_part, a.tot_part, a.ms, a.isig, rsplit, a.C, a.D, a.LD, a.NG, a.Cpad,
+                                               a.dmu, a.coldot_part);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
 
 }  // namespace exvae

@@ -64,6 +64,8 @@ struct PriorWs {
   float* glp;          // [Bpad]
   float* lsp;          // [Bpad]
   int64_t* zip;        // [Bpad]
+  float* gcol_part;    // [rsplit, Cpad, NG]  pass-2 partials when the row blocks are split over CTAs
+  float* tot_part;     // [rsplit, Cpad]
   size_t bytes;
 };
 
@@ -117,6 +119,9 @@ inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
       w.glp = (float*)take(sizeof(float) * w.Bpad);
       w.lsp = (float*)take(sizeof(float) * w.Bpad);
       w.zip = (int64_t*)take(sizeof(int64_t) * w.Bpad);
+      const int rs = prior_bwd_pass2_splits(w.Bpad, w.Cpad);
+      w.gcol_part = rs > 1 ? (float*)take(sizeof(float) * (size_t)rs * w.Cpad * w.NG) : nullptr;
+      w.tot_part = rs > 1 ? (float*)take(sizeof(float) * (size_t)rs * w.Cpad) : nullptr;
     }
   } else {
     w.dzs_part = w.rowsum_part = w.coldot_part = w.rowdot = w.rs = nullptr;
@@ -125,6 +130,7 @@ inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
     w.NG = 0;
     w.zsT = w.msT = w.glp = w.lsp = nullptr;
     w.zip = nullptr;
+    w.gcol_part = w.tot_part = nullptr;
   }
   w.bytes = off;
   return w;
@@ -839,6 +845,7 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
     a.zip = mask ? w.zip : nullptr; a.cidx = w.cidx; a.isig = w.isig;
     a.Bpad = w.Bpad; a.Cpad = w.Cpad; a.KP = w.KP; a.NG = w.NG; a.LD = w.LD; a.B = B; a.C = C; a.D = D;
     a.dzs_part = w.dzs_part; a.rowsum_part = w.rowsum_part; a.dmu = dmu; a.coldot_part = w.coldot_part;
+    a.gcol_part = w.gcol_part; a.tot_part = w.tot_part;
     int nsplit = 0, ntile = 0;
     rc = prior_bwd_tc_launch(a, &nsplit, &ntile, st);
     if (rc) return rc;

@@ -35,7 +35,11 @@ struct PriorBwdTcArgs {
   float* rowsum_part;   // [nsplit, Bpad]       (out) per-split row sums of W
   float* dmu;           // [C, D]               (out)
   float* coldot_part;   // [Cpad/128, LD]       (out) per column tile sum_n dms[n,d]*ms[n,d]
+  float* gcol_part;     // [rsplit, Cpad, NG]   (scratch) pass-2 partials of W^T.zs when the row blocks are split
+  float* tot_part;      // [rsplit, Cpad]       (scratch) pass-2 partial column sums of W
 };
+// row-block splits of pass 2 for this geometry (1 = one CTA per exemplar tile walks all row blocks)
+int prior_bwd_pass2_splits(int Bpad, int Cpad);
 // launches both passes; *nsplit_out = number of dzs/rowsum partials per row, *ntile_out = column tiles of coldot_part
 int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out, cudaStream_t st);
 // transposed hi/lo planes + padded per-row arrays for the backward
