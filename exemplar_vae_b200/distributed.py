@@ -54,6 +54,75 @@ class FlatGrads:
         self.buf.mul_(1.0 / world)
 
 
+class GradBuckets:
+    """Data-parallel gradient averaging in a few contiguous buckets of the flat buffer, each all-reduced
+    (NCCL AVG, asynchronously on the communicator's stream) as soon as the backward has produced every
+    gradient in it, so that the exchange of the decoder / head / layer-2 gradients hides behind the rest of
+    the backward.  Buckets are contiguous parameter ranges in REVERSE registration order (the backward
+    produces the last layers first); the bucket that holds the first-registered parameters completes last and
+    is issued by ``finish()``, on the caller's stream after ``backward()`` has joined every side stream."""
+
+    def __init__(self, flat: FlatGrads, group=None, n_buckets: int = 3):
+        self.flat, self.group = flat, group
+        self._avg = dist.get_backend(group) == "nccl"      # gloo (CPU tests) has no AVG: sum, then scale in finish()
+        total = flat.buf.numel()
+        target = max(1, total // n_buckets)
+        self.ranges, self.bucket_of = [], {}
+        off, lo, acc = 0, 0, 0
+        for i, p in enumerate(flat.params):
+            n = p.numel()
+            self.bucket_of[p.grad.data_ptr()] = len(self.ranges)
+            off += n
+            acc += n
+            if acc >= target and len(self.ranges) < n_buckets - 1 and i + 1 < len(flat.params):
+                self.ranges.append((lo, off))
+                lo, acc = off, 0
+        self.ranges.append((lo, off))
+        self.totals = [0] * len(self.ranges)
+        for b in self.bucket_of.values():
+            self.totals[b] += 1
+        self.pending = list(self.totals)
+        self.works = []
+        self.fired = [False] * len(self.ranges)
+        # gradients that reach .grad through autograd's own accumulation are only COUNTED here: AccumulateGrad may run
+        # on a stream outside a CUDA-graph capture, so a collective is never issued from this hook (the next fused
+        # dense backward, or finish(), issues every bucket that has become complete)
+        for p in flat.params:
+            p.register_post_accumulate_grad_hook(lambda t: self.ready(t.grad, may_fire=False))
+
+    def reset(self):
+        self.pending = list(self.totals)
+        self.fired = [False] * len(self.ranges)
+        self.works = []
+
+    def _fire(self, b):
+        lo, hi = self.ranges[b]
+        self.fired[b] = True
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self.works.append(dist.all_reduce(self.flat.buf[lo:hi], op=op, group=self.group, async_op=True))
+
+    def ready(self, grad, may_fire=True):
+        """``grad`` (a view of the flat buffer) is final for this step."""
+        b = self.bucket_of.get(grad.data_ptr())
+        if b is None:
+            return
+        self.pending[b] -= 1
+        if may_fire:
+            for k in range(len(self.ranges) - 1, 0, -1):         # bucket 0 is always issued by finish()
+                if self.pending[k] <= 0 and not self.fired[k]:
+                    self._fire(k)
+
+    def finish(self):
+        for b in range(len(self.ranges) - 1, -1, -1):
+            if not self.fired[b]:
+                self._fire(b)
+        for w in self.works:
+            w.wait()
+        if not self._avg:
+            self.flat.buf.mul_(1.0 / dist.get_world_size(self.group))
+        self.reset()
+
+
 def shard_bank(model, optimizer=None, group=None, shard=True):
     """Switch ``model`` to a range-sharded exemplar bank + data-parallel gradients over ``group``.
     ``shard=False`` keeps the bank replicated (pure data parallelism: every rank draws all N exemplars /
@@ -68,5 +137,13 @@ def shard_bank(model, optimizer=None, group=None, shard=True):
     for p in model.parameters():
         dist.broadcast(p.data, src=0, group=group)
     model.flat_grads = FlatGrads(model.parameters())
-    model.grad_sync = lambda: model.flat_grads.all_reduce_mean(group)
+    import os
+    if os.environ.get("EXVAE_GRAD_SYNC", "buckets") == "single":      # one blocking all-reduce after the backward
+        model.grad_sync = lambda: model.flat_grads.all_reduce_mean(group)
+        return model
+    buckets = GradBuckets(model.flat_grads, group)
+    model.grad_buckets = buckets
+    from . import ops
+    ops.set_grad_ready_hook(buckets.ready)       # dense layers report their in-kernel accumulated gradients
+    model.grad_sync = buckets.finish
     return model

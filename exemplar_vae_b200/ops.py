@@ -424,6 +424,7 @@ class _GatedDense(torch.autograd.Function):
                 "gated_dense_bwd")
         _count(3 + (1 if dx is not None else 0))
         if sink is not None:
+            _sink_done(sink)
             return dx, None, None, None, None, None
         return dx, dWh, dbh, dWg, dbg, None
 
@@ -448,6 +449,19 @@ def _grad_sink(*params):
 
 
 _FUSE_GRAD_ACCUM = False
+_GRAD_READY_HOOK = None      # called with each .grad buffer a fused dense backward has just completed (distributed.GradBuckets)
+
+
+def set_grad_ready_hook(fn) -> None:
+    global _GRAD_READY_HOOK
+    _GRAD_READY_HOOK = fn
+
+
+def _sink_done(sink) -> None:
+    if _GRAD_READY_HOOK is not None:
+        for g in sink:
+            if g is not None:
+                _GRAD_READY_HOOK(g)
 
 
 def set_fused_grad_accumulation(on: bool) -> bool:
@@ -504,6 +518,7 @@ class _Linear(torch.autograd.Function):
                                    1 if sink is not None else 0, _stream()), "linear_bwd")
         _count(3 + (1 if dx is not None else 0))
         if sink is not None:
+            _sink_done(sink)
             return dx, None, None, None, None, None, None
         return dx, dW, db, None, None, None, None
 
@@ -821,15 +836,18 @@ class _PriorLSESharded(torch.autograd.Function):
         C = mu.shape[0]
         masked = z_idx is not None and mu_idx is not None
         z_all = torch.empty((G * B, D), dtype=torch.float32, device=z.device)
-        dist.all_gather_into_tensor(z_all, z, group=group)
         zi_all = None
         if masked:
             z_idx = _i64(z_idx).reshape(-1)
             mu_idx = _i64(mu_idx).reshape(-1)
             zi_all = torch.empty((G * B,), dtype=torch.int64, device=z.device)
+            # (torch's _coalescing_manager would make this one NCCL launch, but it breaks CUDA-graph capture:
+            #  "dependency created on uncaptured work in another stream", torch 2.11)
+            dist.all_gather_into_tensor(z_all, z, group=group)
             dist.all_gather_into_tensor(zi_all, z_idx, group=group)
         else:
             mu_idx = None
+            dist.all_gather_into_tensor(z_all, z, group=group)
         Bt = G * B
         ws = _ws(L.exvae_prior_lse_workspace_bytes(Bt, C, D), z.device)
         stats = torch.empty((Bt, 4), dtype=torch.float32, device=z.device)

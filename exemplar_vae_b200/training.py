@@ -77,7 +77,10 @@ class GraphedTrainStep:
         if getattr(model, "flat_grads", None) is None:
             from .distributed import FlatGrads
             model.flat_grads = FlatGrads(model.parameters())     # stable grad pointers, one memset per step
-        model.overlap_prior = True                               # prior || decoder as parallel graph branches
+        import os
+        # prior || decoder as parallel graph branches (EXVAE_OVERLAP_SHARDED=0: only with a replicated bank)
+        model.overlap_prior = (getattr(model, "bank_group", None) is None
+                               or os.environ.get("EXVAE_OVERLAP_SHARDED", "1") != "0")
         model.train()
         saved = self._snapshot()
         # eager warm-up on a side stream (allocator + optimizer state + grad buffers settle)
