@@ -82,8 +82,9 @@ class BaseModel(nn.Module, ABC):
         self.grad_sync = None                       # set by distributed.shard_bank: averages the flat gradient buffer
         self.fuse_exemplar_encoder = True           # encode batch + exemplars in ONE pass of the shared trunk
         self.overlap_prior = False                  # run the prior term on a side stream next to the decoder (AbsModel)
-        self._z_event = None
-        self._emb_before_z = False                  # exemplar embedding was produced BEFORE z on the main stream
+        self._prior_ctx = None                      # (embedding, x_indices) announced by calculate_loss for the side branch
+        self._log_p_z_early = None
+        self._log_q_early = None                    # log q(z|x) computed together with z in forward()
         self._side_streams = {}
         self._zero_rows = {}
         self._resident_cache = {}
@@ -158,14 +159,16 @@ class BaseModel(nn.Module, ABC):
         """models/BaseModel.py:65-77 — returns (loss, RE, KL): scalars if ``average`` else [B]."""
         x, x_indices = x
         zq = None
-        self._z_event = None             # never reuse a fork point recorded by an earlier forward()
-        self._emb_before_z = exemplars_embedding is not None
+        self._prior_ctx = self._log_p_z_early = self._log_q_early = None
         if (self.fuse_exemplar_encoder and exemplars_embedding is None and dataset is not None
                 and self.args.prior == 'exemplar_prior' and self.args.approximate_prior is False):
             # B200-first: the reference encodes the batch (q_z(x)) and the N exemplars (q_z(.., prior=True))
             # in two passes of the same trunk; here they share one GEMM chain over B+N rows.
             zq, exemplars_embedding = self.q_z_with_exemplars(x, dataset)
-            self._emb_before_z = True
+        if (self.overlap_prior and exemplars_embedding is not None and self.args.prior == 'exemplar_prior'
+                and isinstance(exemplars_embedding, tuple)):
+            # the embedding precedes z on this stream: forward() may fork the prior term next to the decoder
+            self._prior_ctx = (exemplars_embedding, x_indices)
         x_mean, x_logvar, latent_stats = self.forward(x, zq=zq)
         RE = self.reconstruction_loss(x.reshape(x_mean.shape), x_mean, x_logvar)
         KL = self.kl_loss(latent_stats, exemplars_embedding, dataset, cache, x_indices)
@@ -188,6 +191,12 @@ class BaseModel(nn.Module, ABC):
             eps = self._next_eps(mu.shape, mu.device, sub)
         return ops.reparameterize(mu, logvar.expand_as(mu), eps)
 
+    def _reparam_with_logq(self, mu, logvar, sub=0):
+        """(z, log q(z|x)) in one kernel each way: ``reparameterize`` followed by the ``log_normal_diag(z, mu, logvar)``
+        that kl_loss evaluates (models/AbsModel.py:18, models/AbsHModel.py:21,27), bit-identical to the two calls."""
+        eps = self._next_eps(mu.shape, mu.device, sub)
+        return ops.reparam_logq(mu, logvar.expand_as(mu), eps)
+
     # ------------------------------------------------------------------ exemplar prior
     def _bank_logvar_row(self, center_log_variance):
         """Row 0 of the bank's log-variance (models/BaseModel.py:101).  When the bank is the learned scalar broadcast
@@ -198,7 +207,7 @@ class BaseModel(nn.Module, ABC):
         plv = getattr(self, "prior_log_variance", None)
         if (plv is not None and center_log_variance.stride() == (0, 0)
                 and center_log_variance.data_ptr() == plv.data_ptr()):
-            return plv.expand(center_log_variance.shape[1])
+            return ops.bcast_scalar(plv, center_log_variance.shape[1])   # [D] row; the gradient sum is one kernel
         return center_log_variance[0, :]
 
     def _zeros_row(self, P, device):
@@ -217,30 +226,42 @@ class BaseModel(nn.Module, ABC):
         return ops.prior_logprob_matrix(z, centers, lv, z_indices if masked else None,
                                         center_indices if masked else None)
 
+    def _fork_prior(self, z_q):
+        """Called by forward() right after z is available: when calculate_loss has announced the exemplar embedding
+        (``_prior_ctx``), start log p(z) on a side stream HERE, before the decoder is enqueued.
+
+        The prior term and the decoder are independent chains between z and the loss, and the decoder's GEMMs over B
+        rows leave most SMs idle.  Creating the prior ops BEFORE the decoder ops matters for the backward: autograd
+        runs nodes in reverse creation order and makes the consumer stream wait for a producer stream as soon as the
+        producing node has been issued, so a prior branch created last would be issued first and serialise the whole
+        decoder backward behind it (measured: 85 us of an 858 us step).  Only used when the embedding was enqueued
+        before z on the main stream (fused batch+exemplar encoder pass, or a bank handed in by the caller).  A capturing
+        stream turns the fork into two parallel graph branches; with a range-sharded bank the branch also carries the
+        LSE-partial exchange."""
+        ctx, self._prior_ctx = self._prior_ctx, None
+        self._log_p_z_early = None
+        if ctx is None or not z_q.is_cuda:
+            return
+        exemplars_embedding, x_indices = ctx
+        cur = torch.cuda.current_stream()
+        side = self._prior_stream()
+        centers, clv, cidx = exemplars_embedding
+        emb = (centers, self._bank_logvar_row(clv), cidx)     # the parameter's view is taken on the main stream
+        c_total = getattr(exemplars_embedding, "c_total", None)
+        if c_total is not None:
+            from .distributed import ShardedBank
+            emb = ShardedBank(emb, c_total)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=emb)
+        self._log_p_z_early = (log_p_z, side)
+
     def _log_p_z_branch(self, z_q, x_indices, exemplars_embedding):
-        """log p(z) of the exemplar prior, on a side stream next to the decoder when ``overlap_prior`` recorded a
-        fork point in forward()."""
-        ev, self._z_event = self._z_event, None
-        if (ev is not None and self._emb_before_z and self.args.prior == 'exemplar_prior'
-                and isinstance(exemplars_embedding, tuple)):
-            # The prior term and the decoder are independent chains between z and the loss, and the decoder's
-            # GEMMs over B rows leave most SMs idle: run K1 on a side stream forked at the point where z became
-            # available.  Only when the exemplar embedding was enqueued BEFORE that point on the main stream (the
-            # fused batch+exemplar encoder pass, or a bank handed in by the caller): an embedding built afterwards
-            # (get_exemplar_set above) is not ordered before the fork event.  Autograd replays the same fork in the
-            # backward (each node runs on its forward stream), and a capturing stream turns it into two parallel
-            # graph branches.  With a range-sharded bank the branch also carries the LSE-partial exchange.
+        """log p(z) of the exemplar prior: the result of the side-stream branch forked in forward(), else computed here."""
+        early, self._log_p_z_early = self._log_p_z_early, None
+        if early is not None:
+            log_p_z, side = early
             cur = torch.cuda.current_stream()
-            side = self._prior_stream()
-            centers, clv, cidx = exemplars_embedding
-            emb = (centers, self._bank_logvar_row(clv), cidx)     # the parameter's view is taken on this stream
-            c_total = getattr(exemplars_embedding, "c_total", None)
-            if c_total is not None:
-                from .distributed import ShardedBank
-                emb = ShardedBank(emb, c_total)
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=emb)
             cur.wait_stream(side)
             log_p_z.record_stream(cur)
             return log_p_z
@@ -455,7 +476,9 @@ class AbsModel(BaseModel):
         if exemplars_embedding is None and self.args.prior == 'exemplar_prior':
             exemplars_embedding = self.get_exemplar_set(z_q_mean, z_q_logvar, dataset, cache, x_indices)
         log_p_z = self._log_p_z_branch(z_q, x_indices, exemplars_embedding)
-        log_q_z = log_normal_diag(z_q, z_q_mean, z_q_logvar, dim=1)
+        log_q_z, self._log_q_early = self._log_q_early, None     # computed together with z in forward()
+        if log_q_z is None:
+            log_q_z = log_normal_diag(z_q, z_q_mean, z_q_logvar, dim=1)
         return ops.lincomb((-1.0, 1.0), log_p_z, log_q_z)     # -(log_p_z - log_q_z)
 
     def generate_x_from_z(self, z, with_reparameterize=True):
@@ -480,9 +503,12 @@ class AbsModel(BaseModel):
             x_mean = flat_chw(x_mean)
         else:
             h = self.p_x_layers(z)
-            x_mean = self.p_x_mean(h)
             if self.args.input_type != 'binary' and self.args.use_logit is False:
-                x_mean = torch.clamp(x_mean, min=0. + 1. / 512., max=1. - 1. / 512.)
+                from ._lib import ACT_HARDTANH       # the clamp of models/AbsModel.py:36 fused in the GEMM epilogue
+                lin = self.p_x_mean.linear
+                x_mean = ops.linear(h, lin.weight, lin.bias, ACT_HARDTANH, 0. + 1. / 512., 1. - 1. / 512.)
+            else:
+                x_mean = self.p_x_mean(h)
         if self.args.input_type == 'binary':
             x_logvar = self._zeros_row(P, x_mean.device)
         else:
@@ -491,10 +517,10 @@ class AbsModel(BaseModel):
 
     def forward(self, x, label=0, num_categories=10, zq=None):
         z_q_mean, z_q_logvar = self.q_z(x) if zq is None else zq
-        z_q = self.reparameterize(z_q_mean, z_q_logvar)
-        if self.overlap_prior and z_q.is_cuda:
-            self._z_event = torch.cuda.current_stream().record_event()   # fork point of the prior branch (kl_loss)
-        x_mean, x_logvar = self.p_x(z_q)
+        z_q, self._log_q_early = self._reparam_with_logq(z_q_mean, z_q_logvar)
+        z_dec, z_q = ops.fanout(z_q, 2)           # consumers: decoder | prior term
+        self._fork_prior(z_q)
+        x_mean, x_logvar = self.p_x(z_dec)
         return x_mean, x_logvar, (z_q, z_q_mean, z_q_logvar)
 
 
@@ -506,10 +532,13 @@ class BaseHModel(BaseModel):
         if exemplars_embedding is None and self.args.prior == 'exemplar_prior':
             exemplars_embedding = self.get_exemplar_set(z2_q_mean, z2_q_logvar, dataset, cache, x_indices)
         D1, D2 = self.args.z1_size, self.args.z2_size
+        early, self._log_q_early = self._log_q_early, None       # (log_q_z2, log_q_z1) computed with z2 / z1 in forward()
         log_p_z1 = log_normal_diag(z1_q.view(-1, D1), z1_p_mean.view(-1, D1), z1_p_logvar.view(-1, D1), dim=1)
-        log_q_z1 = log_normal_diag(z1_q.view(-1, D1), z1_q_mean.view(-1, D1), z1_q_logvar.view(-1, D1), dim=1)
+        log_q_z1 = early[1] if early is not None else \
+            log_normal_diag(z1_q.view(-1, D1), z1_q_mean.view(-1, D1), z1_q_logvar.view(-1, D1), dim=1)
         log_p_z2 = self._log_p_z_branch(z2_q, x_indices, exemplars_embedding)
-        log_q_z2 = log_normal_diag(z2_q.view(-1, D2), z2_q_mean.view(-1, D2), z2_q_logvar.view(-1, D2), dim=1)
+        log_q_z2 = early[0] if early is not None else \
+            log_normal_diag(z2_q.view(-1, D2), z2_q_mean.view(-1, D2), z2_q_logvar.view(-1, D2), dim=1)
         return ops.lincomb((-1.0, -1.0, 1.0, 1.0), log_p_z1, log_p_z2, log_q_z1, log_q_z2)
 
     def generate_x_from_z(self, z, with_reparameterize=True):
@@ -528,14 +557,14 @@ class BaseHModel(BaseModel):
         else:
             x = self.q_z1_layers_x(x)
         z2 = self.q_z1_layers_z2(z2)
-        h = torch.cat((x, z2), 1)
+        h = ops.concat_cols(x, z2)
         h = self.q_z1_layers_joint(h)
         return self.q_z1_mean(h), self.q_z1_logvar(h)
 
     def p_x(self, z1, z2, x=None):
         z1 = self.p_x_layers_z1(z1)
         z2 = self.p_x_layers_z2(z2)
-        h = torch.cat((z1, z2), 1)
+        h = ops.concat_cols(z1, z2)
         conv = 'convhvae_2level' in self.args.model_name
         if conv:
             h = self.p_x_layers_joint_pre(h)
@@ -556,11 +585,13 @@ class BaseHModel(BaseModel):
 
     def forward(self, x, zq=None):
         z2_q_mean, z2_q_logvar = self.q_z(x) if zq is None else zq
-        z2_q = self.reparameterize(z2_q_mean, z2_q_logvar, sub=0)
-        if self.overlap_prior and z2_q.is_cuda:
-            self._z_event = torch.cuda.current_stream().record_event()   # fork point of the prior branch (kl_loss)
-        z1_q_mean, z1_q_logvar = self.q_z1(x, z2_q)
-        z1_q = self.reparameterize(z1_q_mean, z1_q_logvar, sub=1)
-        z1_p_mean, z1_p_logvar = self.p_z1(z2_q)
-        x_mean, x_logvar = self.p_x(z1_q, z2_q)
+        z2_q, log_q_z2 = self._reparam_with_logq(z2_q_mean, z2_q_logvar, sub=0)
+        z2_a, z2_b, z2_c, z2_q = ops.fanout(z2_q, 4)     # consumers: q(z1|x,z2) | p(z1|z2) | p(x|z1,z2) | prior term
+        self._fork_prior(z2_q)
+        z1_q_mean, z1_q_logvar = self.q_z1(x, z2_a)
+        z1_q, log_q_z1 = self._reparam_with_logq(z1_q_mean, z1_q_logvar, sub=1)
+        z1_a, z1_q = ops.fanout(z1_q, 2)                 # consumers: p(x|z1,z2) | log p(z1|z2)
+        self._log_q_early = (log_q_z2, log_q_z1)
+        z1_p_mean, z1_p_logvar = self.p_z1(z2_b)
+        x_mean, x_logvar = self.p_x(z1_a, z2_c)
         return x_mean, x_logvar, (z1_q, z1_q_mean, z1_q_logvar, z2_q, z2_q_mean, z2_q_logvar, z1_p_mean, z1_p_logvar)

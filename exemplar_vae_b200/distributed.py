@@ -46,7 +46,11 @@ class FlatGrads:
             off += n
 
     def zero_(self):
-        self.buf.zero_()
+        if self.buf.is_cuda:
+            from . import ops
+            ops.zero_(self.buf)          # cudaMemsetAsync through the C ABI (no ATen fill kernel on the step)
+        else:
+            self.buf.zero_()
 
     def all_reduce_mean(self, group=None):
         world = dist.get_world_size(group)

@@ -369,7 +369,12 @@ class _SharedRows(torch.autograd.Function):
         if g_head is not None:
             if not g_full.is_contiguous():
                 g_full = g_full.contiguous()
-            g_full[:ctx.B].add_(g_head)
+            L = lib()
+            head = g_full[:ctx.B]
+            g_head = _f32(g_head)
+            L.check(L.exvae_lincomb4(_p(head), _p(g_head), None, None, 1.0, 1.0, 0.0, 0.0, head.numel(), _p(head),
+                                     _stream()), "shared_rows_bwd")
+            _count(1)
         return g_full, None
 
 
@@ -461,7 +466,7 @@ def _sink_done(sink) -> None:
     if _GRAD_READY_HOOK is not None:
         for g in sink:
             if g is not None:
-                _GRAD_READY_HOOK(g)
+                _GRAD_READY_HOOK(g, True)
 
 
 def set_fused_grad_accumulation(on: bool) -> bool:
@@ -557,6 +562,145 @@ class _Reparam(torch.autograd.Function):
 
 def reparameterize(mu, logvar, eps) -> torch.Tensor:
     return _Reparam.apply(mu, logvar, eps)
+
+
+class _ReparamLogQ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        L = lib()
+        mu, logvar, eps = _f32(mu), _f32(logvar), _f32(eps)
+        B, D = mu.shape
+        z = torch.empty_like(mu)
+        logq = torch.empty((B,), dtype=torch.float32, device=mu.device)
+        L.check(L.exvae_reparam_logq_fwd(_p(mu), _p(logvar), _p(eps), B, D, _p(z), _p(logq), _stream()), "reparam_logq")
+        _count(1)
+        ctx.save_for_backward(mu, logvar, eps, z)
+        return z, logq
+
+    @staticmethod
+    def backward(ctx, dz, dlogq):
+        L = lib()
+        mu, logvar, eps, z = ctx.saved_tensors
+        B, D = mu.shape
+        dz = _f32(dz) if dz is not None else None
+        dlogq = _f32(dlogq) if dlogq is not None else None
+        dmu = torch.empty_like(mu) if ctx.needs_input_grad[0] else None
+        dlv = torch.empty_like(mu) if ctx.needs_input_grad[1] else None
+        if dmu is None and dlv is None:
+            return None, None, None
+        L.check(L.exvae_reparam_logq_bwd(_p(mu), _p(logvar), _p(eps), _p(z), _p(dz), _p(dlogq), B, D, _p(dmu), _p(dlv),
+                                         _stream()), "reparam_logq_bwd")
+        _count(1)
+        return dmu, dlv, None
+
+
+def reparam_logq(mu, logvar, eps):
+    """(z, log q(z|x)): reparameterize (models/BaseModel.py:79-82) and log_normal_diag(z, mu, logvar, dim=1)
+    (utils/distributions.py:28-33) in one kernel each way; bit-identical to the separate calls."""
+    return _ReparamLogQ.apply(mu, logvar, eps)
+
+
+class _Fanout(torch.autograd.Function):
+    """n aliases of one tensor whose backward sums the n gradients in ONE exvae kernel (autograd's own accumulation
+    would launch n-1 ATen add kernels)."""
+
+    @staticmethod
+    def forward(ctx, t, n):
+        return tuple(t.view_as(t) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        L = lib()
+        gs = [_f32(g) for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        out = torch.empty_like(gs[0])
+        ptrs = [_p(g) for g in gs] + [None] * (4 - len(gs))
+        cs = [1.0] * len(gs) + [0.0] * (4 - len(gs))
+        L.check(L.exvae_lincomb4(*ptrs, *cs, out.numel(), _p(out), _stream()), "fanout_bwd")
+        _count(1)
+        return out, None
+
+
+def fanout(t: torch.Tensor, n: int):
+    assert 2 <= n <= 4
+    return _Fanout.apply(t, n)
+
+
+class _BcastScalar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, n, sink):
+        L = lib()
+        s = _f32(s, "scalar")
+        assert s.numel() == 1
+        ctx.sink = sink
+        out = torch.empty((n,), dtype=torch.float32, device=s.device)
+        L.check(L.exvae_bcast_scalar(_p(s), n, _p(out), _stream()), "bcast_scalar")
+        _count(1)
+        ctx.shape = s.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        g = _f32(g)
+        sink = ctx.sink
+        dst = sink[0] if sink is not None else torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        L.check(L.exvae_sum_to_scalar(_p(g), g.numel(), _p(dst), 1 if sink is not None else 0, _stream()), "sum_to_scalar")
+        _count(1)
+        if sink is not None:
+            if _GRAD_READY_HOOK is not None:
+                _GRAD_READY_HOOK(sink[0], may_fire=False)     # may run on the prior side stream: count only
+            return None, None, None
+        return dst, None, None
+
+
+def bcast_scalar(s: torch.Tensor, n: int) -> torch.Tensor:
+    """A [1] parameter as a contiguous [n] row (prior_log_variance -> bank log-variance row); the gradient is summed
+    (and, with fused accumulation, added into the parameter's .grad) by one kernel."""
+    return _BcastScalar.apply(s, int(n), _grad_sink(s))
+
+
+class _ConcatCols(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        L = lib()
+        a, b = _f32(a), _f32(b)
+        R, Ka = a.shape
+        Kb = b.shape[1]
+        out = torch.empty((R, Ka + Kb), dtype=torch.float32, device=a.device)
+        L.check(L.exvae_concat_cols_fwd(_p(a), _p(b), R, Ka, Kb, _p(out), _stream()), "concat_cols")
+        _count(1)
+        ctx.dims = (R, Ka, Kb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        R, Ka, Kb = ctx.dims
+        g = _f32(g)
+        da = torch.empty((R, Ka), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        db = torch.empty((R, Kb), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
+        if da is None and db is None:
+            return None, None
+        L.check(L.exvae_concat_cols_bwd(_p(g), R, Ka, Kb, _p(da), _p(db), _stream()), "concat_cols_bwd")
+        _count(1)
+        return da, db
+
+
+def concat_cols(a, b) -> torch.Tensor:
+    """torch.cat((a, b), 1) for two [R, *] matrices (models/AbsHModel.py:55,83)."""
+    return _ConcatCols.apply(a, b)
+
+
+@torch.no_grad()
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    assert t.is_cuda and t.is_contiguous()
+    L = lib()
+    L.check(L.exvae_zero(_p(t), t.numel() * t.element_size(), _stream()), "zero")
+    return t
 
 
 class _LogNormalDiag(torch.autograd.Function):

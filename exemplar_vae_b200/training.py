@@ -70,6 +70,7 @@ class GraphedTrainStep:
         self.indices = torch.zeros(batch_size, 1, dtype=torch.int64, device=dev)
         self.out = torch.zeros(3, dtype=torch.float32, device=dev)
         self.beta_dev = torch.full((1,), float(beta), dtype=torch.float32, device=dev)
+        self._g3 = torch.tensor([1.0, 0.0, 0.0], dtype=torch.float32, device=dev)
         self.rng_override = rng_override
         self.cache = cache
         self.graph = None
@@ -157,7 +158,12 @@ class GraphedTrainStep:
         try:
             loss, RE, KL = model.calculate_loss((x, self.indices), self.beta_dev, average=True, cache=self.cache,
                                                 dataset=self.dataset)
-            loss.backward()
+            base = loss._base            # calculate_loss(average=True) returns three views of one [3] tensor
+            if base is not None and base.numel() == 3:
+                # d(loss) = 1 through the [3] result itself: no ones-fill, no zero-fill + copy of a select backward
+                torch.autograd.backward(base, grad_tensors=self._g3)
+            else:
+                loss.backward()
         finally:
             ops.set_fused_grad_accumulation(prev)
         if model.grad_sync is not None:

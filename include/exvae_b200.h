@@ -195,6 +195,26 @@ EXVAE_API int exvae_reparameterize_fwd(const float* mu, const float* logvar, con
                              exvae_stream_t stream);
 EXVAE_API int exvae_reparameterize_bwd(const float* logvar, const float* eps, const float* dz, int64_t n, float* dmu,
                              float* dlogvar, exvae_stream_t stream);
+/* reparameterize + log q(z|x) in one pass (models/BaseModel.py:79-82 followed by utils/distributions.py:28-33 as
+ * models/AbsModel.py:18 / AbsHModel.py:21,27 call them): z [B,D] and logq [B] = log_normal_diag(z, mu, logvar, dim=1),
+ * bit-identical to the two separate calls.  Backward: dz = gradient reaching z from its other consumers (nullable),
+ * dlogq [B] (nullable) -> dmu, dlogvar (total derivatives through z). */
+EXVAE_API int exvae_reparam_logq_fwd(const float* mu, const float* logvar, const float* eps, int B, int D, float* z,
+                                     float* logq, exvae_stream_t stream);
+EXVAE_API int exvae_reparam_logq_bwd(const float* mu, const float* logvar, const float* eps, const float* z,
+                                     const float* dz, const float* dlogq, int B, int D, float* dmu, float* dlogvar,
+                                     exvae_stream_t stream);
+/* prior_log_variance [1] broadcast to a [n] row (models/BaseModel.py:212-214) and the sum of its gradient
+ * (accumulate != 0: out[0] += sum, for in-place accumulation into the parameter's .grad). */
+EXVAE_API int exvae_bcast_scalar(const float* src, int n, float* out, exvae_stream_t stream);
+EXVAE_API int exvae_sum_to_scalar(const float* src, int n, float* out, int accumulate, exvae_stream_t stream);
+/* torch.cat((a, b), 1) (models/AbsHModel.py:55,83): out [R, Ka+Kb]; backward splits dout (da / db nullable). */
+EXVAE_API int exvae_concat_cols_fwd(const float* a, const float* b, int64_t R, int Ka, int Kb, float* out,
+                                    exvae_stream_t stream);
+EXVAE_API int exvae_concat_cols_bwd(const float* dout, int64_t R, int Ka, int Kb, float* da, float* db,
+                                    exvae_stream_t stream);
+/* zero `bytes` bytes (cudaMemsetAsync): the one gradient-buffer reset of a training step. */
+EXVAE_API int exvae_zero(void* ptr, size_t bytes, exvae_stream_t stream);
 /* log_normal_diag(x, mean, log_var, dim=1) (utils/distributions.py:28-33): out [B]. */
 EXVAE_API int exvae_log_normal_diag_fwd(const float* x, const float* mean, const float* logvar, int B, int D, float* out,
                               exvae_stream_t stream);
