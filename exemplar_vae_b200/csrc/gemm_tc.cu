@@ -60,6 +60,7 @@ struct TcParams {
   float* out0; float* out1; float* out2; int ldc;
   int act; float lo, hi;
   int c_vec;
+  TcPriorEpi prior;            // TC_LSE / TC_PW epilogues
   unsigned long long* trace;   // debug: per-CTA {start, end, tiles, SM} (tools/gemm_trace.py), null in production
 };
 unsigned long long* g_trace = nullptr;
@@ -130,9 +131,15 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   constexpr int B_BYTES = BN * TBK * 4;    // raw (= hi) B tile; the lo tile follows it
   constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   constexpr int B_OFF = A_BYTES;                         // B hi slot inside a stage
-  constexpr uint32_t TM_COLS = 512;                      // 2 accumulators + TSTAGES x (32 hi + 32 lo) A columns
-  constexpr uint32_t TM_A0 = 2 * BN;
-  static_assert(2 * BN + TSTAGES * 64 <= 512, "TMEM budget");
+  // Exemplar-prior epilogues keep TWO accumulators per tile: the hi*hi products in one, the two small cross products
+  // (A_lo*B_hi + A_hi*B_lo, 2^-11 of the main term) in the other, added in fp32 by the epilogue.  The TMEM accumulate
+  // truncates, so the error grows with (number of adds) x ulp(|accumulator|); logits are differences of terms ~|mu/sigma|^2
+  // (1e3 at D=128), and keeping the cross terms out of the big accumulator cuts the truncating adds on it by 3.
+  constexpr bool DUAL = (EPI == TC_LSE || EPI == TC_PW);
+  constexpr int ACC_COLS = DUAL ? 2 * BN : BN;           // TMEM columns per accumulator buffer
+  constexpr uint32_t TM_COLS = 512;                      // 2 accumulator buffers + TSTAGES x (32 hi + 32 lo) A columns
+  constexpr uint32_t TM_A0 = 2 * ACC_COLS;
+  static_assert(2 * ACC_COLS + TSTAGES * 64 <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
   unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -214,7 +221,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         const uint32_t idesc = c.last ? umma_idesc(TBM, c.neff, false, B_MN) : idesc_full;
         mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        const uint32_t d_cross = DUAL ? d_tmem + BN : d_tmem;
         for (int kb = 0; kb < c.nkb; ++kb, ++it) {
           const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
           mbar_wait(&conv[s], ph);
@@ -231,9 +239,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
-            umma_tf32_ts(d_tmem, ta_hi + 32 + 8 * ks, b_hi, idesc, first);           // A_lo x B_hi: small terms first
-            umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_lo, idesc, 1u);                   // A_hi x B_lo
-            umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, 1u);                   // A_hi x B_hi
+            umma_tf32_ts(d_cross, ta_hi + 32 + 8 * ks, b_hi, idesc, first);          // A_lo x B_hi: small terms first
+            umma_tf32_ts(d_cross, ta_hi + 8 * ks, b_lo, idesc, 1u);                  // A_hi x B_lo
+            umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, DUAL ? first : 1u);    // A_hi x B_hi
           }
           umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
@@ -309,6 +317,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     int j = 0;
     // write the staged 32x32 patch to dst[(row0 + r) * ldc + col0 + c] for c < ncols
     auto flush = [&](float* dst, int row0, int col0, int ncols) {
+      const int ldc = (EPI == TC_PW) ? p.prior.ldw : p.ldc;
       __syncwarp();
       if (p.c_vec) {
 #pragma unroll
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           const int r = 4 * i + (lane >> 3), ch = (lane & 7) * 4;
           const float4 v = *reinterpret_cast<const float4*>(patch + r * EP_LD + ch);
           if (row0 + r < p.M) {
-            float* d = dst + (size_t)(row0 + r) * p.ldc + col0 + ch;
+            float* d = dst + (size_t)(row0 + r) * ldc + col0 + ch;
             if (ch + 3 < ncols) {
               *reinterpret_cast<float4*>(d) = v;
             } else {
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         }
       } else {
         if (lane < ncols)
-          for (int r = 0; r < 32 && row0 + r < p.M; ++r) dst[(size_t)(row0 + r) * p.ldc + col0 + lane] = patch[r * EP_LD + lane];
+          for (int r = 0; r < 32 && row0 + r < p.M; ++r) dst[(size_t)(row0 + r) * ldc + col0 + lane] = patch[r * EP_LD + lane];
       }
       __syncwarp();
     };
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       mbar_wait(&acc_full[acc], (j >> 1) & 1);
       tc_fence_after();
       const int row0 = c.m0 + 32 * q;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * ACC_COLS);
       float* prow = patch + lane * EP_LD;
       if (EPI == TC_GATED) {
 #pragma unroll 1
@@ -385,6 +394,76 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             flush(p.out1, row0, col0, ncols);
           }
         }
+      } else if (EPI == TC_LSE || EPI == TC_PW) {
+        // exemplar-prior epilogues: the accumulator holds base-2 logits S[row, col]
+        const int row = row0 + lane;
+        const bool rowok = row < p.M;
+        const bool mask = p.prior.cidx != nullptr;
+        const long long zi = (mask && rowok) ? p.prior.zidx[row] : (long long)0x8000000000000000ull;
+        const int zlo = (int)zi;
+        float m = -INFINITY, ssum = 0.f, cnt = 0.f;
+        float gi = 0.f, li = INFINITY;
+        if (EPI == TC_PW && rowok) { gi = p.prior.g[row]; li = p.prior.lse2[row]; }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col0 = c.n0 + c0;
+          if (col0 >= p.N) break;   // warp-uniform
+          const int ncols = min(32, p.N - col0);
+          uint32_t v[32];
+          {
+            uint32_t vc[32];
+            tmem_ld32(lane_addr + c0, v);              // hi*hi accumulator
+            tmem_ld32(lane_addr + BN + c0, vc);        // cross-term accumulator
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(vc[e]));
+          }
+          int clo = 0;
+          if (mask) clo = lane < ncols ? (int)p.prior.cidx[col0 + lane] : 0;
+          if (EPI == TC_LSE) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float x = e < ncols ? __uint_as_float(v[e]) : -INFINITY;
+              if (mask) {
+                const int ce = __shfl_sync(0xffffffffu, clo, e);
+                if (ce == zlo && e < ncols && rowok && p.prior.cidx[col0 + e] == zi) {   // 32-bit pre-test, rare hit
+                  x = -INFINITY;
+                  cnt += 1.f;
+                }
+              }
+              v[e] = __float_as_uint(x);
+              mx = fmaxf(mx, x);
+            }
+            const float mn = fmaxf(m, mx);
+            const float msafe = (mn == -INFINITY) ? 0.f : mn;
+            float acc = ssum * ex2_approx(m - msafe);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc += ex2_approx(__uint_as_float(v[e]) - msafe);
+            ssum = acc;
+            m = mn;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float w = gi * ex2_approx(__uint_as_float(v[e]) - li);
+              if (mask) {
+                const int ce = __shfl_sync(0xffffffffu, clo, e);
+                if (ce == zlo && e < ncols && rowok && p.prior.cidx[col0 + e] == zi) w = 0.f;
+              }
+              if (li == -INFINITY || e >= ncols) w = 0.f;
+              v[e] = __float_as_uint(w);
+              // transposed copy: lane = row, so one store instruction covers 32 consecutive rows of column col0+e
+              if (rowok && e < ncols) p.prior.wt[(size_t)(col0 + e) * p.prior.ldwt + row] = w;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4*>(prow + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                 __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            flush(p.prior.w, row0, col0, ncols);
+          }
+        }
+        if (EPI == TC_LSE && rowok)
+          reinterpret_cast<float4*>(p.prior.part)[(size_t)row * p.ntn + (c.n0 / BN)] = make_float4(m, ssum, cnt, 0.f);
       } else {
         float* dst_base = (EPI == TC_SPLITK) ? p.out0 + (size_t)c.z * p.M * p.ldc : p.out0;
 #pragma unroll 1
@@ -531,11 +610,17 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   p.gated_O = g.gated_O;
   p.bias0 = g.bias0; p.bias1 = g.bias1; p.out0 = g.out0; p.out1 = g.out1; p.out2 = g.out2; p.ldc = g.ldc;
   p.act = g.act; p.lo = g.lo; p.hi = g.hi;
+  p.prior = g.prior;
   p.trace = g_trace;
   if (g_trace) g_trace += 8 * 160;   // the next traced launch writes the next segment
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.c_vec = (g.ldc % 4 == 0) && al16(g.out0) && (!g.out1 || al16(g.out1)) && (!g.out2 || al16(g.out2)) &&
             (g.epi != TC_SPLITK || ((size_t)g.M * g.ldc) % 4 == 0);
+  if (g.epi == TC_PW) p.c_vec = (g.prior.ldw % 4 == 0) && al16(g.prior.w);
+  if constexpr (BN == 64) {      // the dual-accumulator prior epilogues only exist for 64-wide tiles (TMEM budget)
+    if (g.epi == TC_LSE && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_LSE>(g, ma, mb, mbl, p, st);
+    if (g.epi == TC_PW && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_PW>(g, ma, mb, mbl, p, st);
+  }
   if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, mbl, p, st);
   if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, mbl, p, st);
   if (g.epi == TC_PLAIN && !g.a_mn && g.b_mn) return launch<BN, false, true, TC_PLAIN>(g, ma, mb, mbl, p, st);
@@ -543,13 +628,18 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   return EXVAE_ERR_UNSUPPORTED;
 }
 
+static bool tc_use_bn64(const TcGemm& g) {
+  if (g.epi == TC_LSE || g.epi == TC_PW) return true;     // two accumulators per tile: 2 x 2 x 64 TMEM columns
+  if (g.epi == TC_SPLITK) return false;
+  const int ntn = g.epi == TC_GATED ? ceil_div(g.gated_O, 64) : ceil_div(g.N, 128);
+  return 2 * ceil_div(g.M, TBM) * ntn <= sm_count();
+}
+int tc_gemm_ntn(const TcGemm& g) { return ceil_div(g.N, tc_use_bn64(g) ? 64 : 128); }
+
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   // Small GEMMs (the decoder and the batch-only heads: a few 128-wide tiles) are latency-bound and leave most SMs idle:
   // 64-wide tiles double the number of CTAs and halve each CTA's B-side work and epilogue.
-  if (g.epi != TC_SPLITK) {
-    const int ntn = g.epi == TC_GATED ? ceil_div(g.gated_O, 64) : ceil_div(g.N, 128);
-    if (2 * ceil_div(g.M, TBM) * ntn <= sm_count()) return tc_gemm_launch_bn<64>(g, st);
-  }
+  if (tc_use_bn64(g)) return tc_gemm_launch_bn<64>(g, st);
   return tc_gemm_launch_bn<128>(g, st);
 }
 

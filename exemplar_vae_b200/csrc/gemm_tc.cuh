@@ -5,7 +5,21 @@
 
 namespace exvae {
 
-enum TcEpi { TC_BIAS_ACT = 0, TC_GATED = 1, TC_PLAIN = 2, TC_SPLITK = 3 };
+enum TcEpi { TC_BIAS_ACT = 0, TC_GATED = 1, TC_PLAIN = 2, TC_SPLITK = 3, TC_LSE = 4, TC_PW = 5 };
+
+// Exemplar-prior epilogues (K1 for D >= 64, prior_lse.cu): the GEMM computes S = Z'.M'^T = base-2 logits
+// (rows = latents, columns = exemplars; operands augmented so that no bias term is needed).
+//   TC_LSE: per row and column tile, the (max, sum 2^(S-max), #masked) partial of the log-sum-exp -> part[M][ntn][4]
+//   TC_PW : W = g_row * 2^(S - lse2_row) (0 for leave-one-out pairs) stored as w [M][ldw] AND transposed wt [N][ldwt]
+struct TcPriorEpi {
+  const long long* cidx;   // [N] dataset index per column (null = no mask)
+  const long long* zidx;   // [M] dataset index per row
+  const float* g;          // [M]   TC_PW: upstream gradient
+  const float* lse2;       // [M]   TC_PW: base-2 row log-sum
+  float* part;             // TC_LSE
+  float* w; int ldw;       // TC_PW
+  float* wt; int ldwt;     // TC_PW
+};
 
 // D[M,N] = A[M,K] * B[N,K]^T (+ epilogue).  Operands are plain fp32 row-major matrices [rows][cols] (16-byte aligned
 // base and row pitch); the kernel splits them into tf32 hi/lo parts in shared memory.
@@ -21,6 +35,7 @@ struct TcGemm {
   float* out0; float* out1; float* out2; int ldc;
   int act; float lo, hi;
   int splits, kchunk;  // TC_SPLITK: grid.z = splits, out0 = partial [splits][M][N]
+  TcPriorEpi prior;    // TC_LSE / TC_PW
 };
 
 bool tc_enabled();                       // sm_100 device, driver entry point found, not disabled by EXVAE_GEMM=simt
@@ -28,6 +43,7 @@ bool tc_dims_ok(int rows_pitch_elems);   // TMA needs 16-byte row pitches
 void tc_set_trace(unsigned long long* buf);   // debug: 8 u64 per CTA of the NEXT launches (null = off)
 unsigned long long* tc_take_trace(size_t words);   // debug: current trace segment (or null), then advance by `words`
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st);
+int tc_gemm_ntn(const TcGemm& g);        // number of column tiles tc_gemm_launch will use for this problem (TC_LSE partials)
 // out[0..n) = w0, out[n..2n) = w1 (the two weight tensors of a gated layer as one [2*O, K] operand); n % 4 == 0
 int tc_concat2(const float* w0, const float* w1, size_t n, float* out, cudaStream_t st);
 

@@ -24,6 +24,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "prior_lse_tc.cuh"
 
 namespace exvae {
@@ -66,6 +67,19 @@ struct PriorWs {
   int64_t* zip;        // [Bpad]
   float* gcol_part;    // [rsplit, Cpad, NG]  pass-2 partials when the row blocks are split over CTAs
   float* tot_part;     // [rsplit, Cpad]
+  // D >= 64: K1 through the persistent 3xTF32 GEMM kernel with prior epilogues (gemm_tc.cu TC_LSE / TC_PW)
+  int gemm;            // 1 = this path is used
+  int KA;              // augmented K = D + 2 rounded up to 4
+  int ldw, ldwt;       // pitches of W [B][ldw] and W^T [C][ldwt]
+  int S1, kchunk1;     // split of the contraction over C (dzs' = W.M')
+  int S2, kchunk2;     // split of the contraction over B (dms' = W^T.Z')
+  float* zaug;         // [B, KA]   (zs*log2e | 1 | 0 | 0..)
+  float* maug;         // [C, KA]   (ms | nb2 | 1 | 0..)
+  float* gpart;        // [B, ceil(C/64), 4] per column-tile LSE partials
+  float* wmat;         // [B, ldw]
+  float* wtmat;        // [C, ldwt]
+  float* p1;           // [S1, B, KA]
+  float* p2;           // [S2, C, KA]
   size_t bytes;
 };
 
@@ -97,6 +111,25 @@ inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
   w.isig = (float*)take(sizeof(float) * w.LD);
   w.part = (float*)take(sizeof(float) * 4 * (size_t)w.Bpad * (size_t)std::max(w.nsplit, 2 * sm_count()));
   w.KP = (D + 1 <= 64) ? ceil_div(D + 1, 8) * 8 : 0;
+  w.gemm = (!w.KP && prior_tc_enabled() && tc_enabled()) ? 1 : 0;
+  w.KA = ceil_div(D + 2, 4) * 4;
+  w.ldw = ceil_div(C, 4) * 4;
+  w.ldwt = ceil_div(B, 4) * 4;
+  {
+    const int tiles1 = ceil_div(B, 128) * ceil_div(w.KA, 128);
+    const int want = std::max(1, sm_count() / std::max(tiles1, 1));
+    w.kchunk1 = std::min(2560, std::max(32, ceil_div(ceil_div(C, want), 32) * 32));
+    w.S1 = ceil_div(C, w.kchunk1);
+    w.S2 = ceil_div(B, 2560);
+    w.kchunk2 = ceil_div(ceil_div(B, w.S2), 32) * 32;
+    w.S2 = ceil_div(B, w.kchunk2);
+  }
+  w.zaug = w.maug = w.gpart = w.wmat = w.wtmat = w.p1 = w.p2 = nullptr;
+  if (w.gemm) {
+    w.zaug = (float*)take(sizeof(float) * (size_t)B * w.KA);
+    w.maug = (float*)take(sizeof(float) * (size_t)C * w.KA);
+    w.gpart = (float*)take(sizeof(float) * 4 * (size_t)B * ceil_div(C, 64));
+  }
   if (w.KP) {
     w.zp = (float*)take(sizeof(float) * 2 * (size_t)w.Bpad * w.KP);
     w.mp = (float*)take(sizeof(float) * 2 * (size_t)w.Cpad * w.KP);
@@ -106,7 +139,17 @@ inline PriorWs prior_ws_layout(int B, int C, int D, bool need_bwd, void* base) {
     w.zp = w.mp = nullptr;
     w.mcnt = w.mlist = nullptr;
   }
-  if (need_bwd) {
+  if (need_bwd && w.gemm) {
+    w.dzs_part = w.rowsum_part = nullptr;
+    w.coldot_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.LD);
+    w.rowdot = (float*)take(sizeof(float) * (size_t)w.Bpad * w.LD);
+    w.rs = (float*)take(sizeof(float) * w.Bpad);
+    w.wmat = (float*)take(sizeof(float) * (size_t)B * w.ldw);
+    w.wtmat = (float*)take(sizeof(float) * (size_t)C * w.ldwt);
+    w.p1 = (float*)take(sizeof(float) * (size_t)w.S1 * B * w.KA);
+    w.p2 = (float*)take(sizeof(float) * (size_t)w.S2 * C * w.KA);
+    w.NG = 0;
+  } else if (need_bwd) {
     w.dzs_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.Bpad * w.LD);
     w.rowsum_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.Bpad);
     w.coldot_part = (float*)take(sizeof(float) * (size_t)w.ntile * w.LD);
@@ -149,10 +192,8 @@ __global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restric
                                                           float* __restrict__ mp, int* __restrict__ mcnt) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (blockIdx.x == 0 && threadIdx.x < LD) {
-    const int d = threadIdx.x;
-    isig[d] = d < D ? 1.0f / expf(0.5f * logvar[d]) : 0.f;
-  }
+  if (blockIdx.x == 0)
+    for (int d = threadIdx.x; d < LD; d += blockDim.x) isig[d] = d < D ? 1.0f / expf(0.5f * logvar[d]) : 0.f;
   if (row >= Cpad + Bpad) return;
   const bool is_bank = row < Cpad;
   const int r = is_bank ? row : row - Cpad;
@@ -733,6 +774,107 @@ __global__ void __launch_bounds__(256) prior_bwd_dlogvar_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------- D >= 64: GEMM-kernel path
+// augmented operands of the logit GEMM:  Z'[b] = (zs_b*log2e | 1 | 0 | 0..)   M'[n] = (ms_n | nb2_n | 1 | 0..)
+//   Z'.M'^T = logit2 ;  W.M' = (sum_n W ms | . | rowsum) ;  W^T.Z' = (log2e * sum_b W zs | colsum | 0)
+__global__ void __launch_bounds__(256) prior_aug_kernel(const float* __restrict__ zs, const float* __restrict__ ms,
+                                                        const float* __restrict__ nb2, int B, int C, int D, int LD,
+                                                        int KA, float* __restrict__ zaug, float* __restrict__ maug) {
+  const long long total = (long long)(B + C) * KA;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / KA;
+    const int k = (int)(e - r * KA);
+    if (r < C) {
+      float v = 0.f;
+      if (k < D) v = ms[(size_t)r * LD + k];
+      else if (k == D) v = nb2[r];
+      else if (k == D + 1) v = 1.f;
+      maug[e] = v;
+    } else {
+      const long long b = r - C;
+      float v = 0.f;
+      if (k < D) v = zs[(size_t)b * LD + k] * kLog2e;
+      else if (k == D) v = 1.f;
+      zaug[(size_t)b * KA + k] = v;
+    }
+  }
+}
+
+// one warp per latent row: sum the split partials of W.M', then dz, rowdot, rs
+__global__ void __launch_bounds__(256) prior_gemm_rows_kernel(const float* __restrict__ p1, int S1, const float* __restrict__ zs,
+                                                              const float* __restrict__ isig, int B, int D, int LD, int KA,
+                                                              float* __restrict__ dz, float* __restrict__ rowdot,
+                                                              float* __restrict__ rs) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const size_t plane = (size_t)B * KA;
+  float rowsum = 0.f;
+  for (int s = 0; s < S1; ++s) rowsum += p1[(size_t)s * plane + (size_t)b * KA + D + 1];
+  for (int d = lane; d < LD; d += 32) {
+    float rd = 0.f;
+    if (d < D) {
+      float a = 0.f;
+      for (int s = 0; s < S1; ++s) a += p1[(size_t)s * plane + (size_t)b * KA + d];
+      const float zv = zs[(size_t)b * LD + d];
+      const float dzs = a - zv * rowsum;
+      dz[(size_t)b * D + d] = dzs * isig[d];
+      rd = dzs * zv;
+    }
+    rowdot[(size_t)b * LD + d] = rd;
+  }
+  if (lane == 0) rs[b] = rowsum;
+}
+
+// one CTA (128 threads = exemplar rows) per tile: sum the split partials of W^T.Z', then dmu and the tile's coldot
+__global__ void __launch_bounds__(128) prior_gemm_cols_kernel(const float* __restrict__ p2, int S2, const float* __restrict__ ms,
+                                                              const float* __restrict__ isig, int C, int D, int LD, int KA,
+                                                              float* __restrict__ dmu, float* __restrict__ coldot_part) {
+  extern __shared__ float red_dyn[];       // [4][LD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x * 128 + tid;
+  const bool ok = n < C;
+  const size_t plane = (size_t)C * KA;
+  float colsum = 0.f;
+  if (ok)
+    for (int s = 0; s < S2; ++s) colsum += p2[(size_t)s * plane + (size_t)n * KA + D];
+  for (int d = 0; d < LD; ++d) {
+    float pd = 0.f;
+    if (d < D && ok) {
+      float g = 0.f;
+      for (int s = 0; s < S2; ++s) g += p2[(size_t)s * plane + (size_t)n * KA + d];
+      const float mv = ms[(size_t)n * LD + d];
+      const float dv = g * kLn2 - colsum * mv;            // Z' carries zs*log2e: undo the factor
+      dmu[(size_t)n * D + d] = dv * isig[d];
+      pd = dv * mv;
+    }
+    pd = warp_sum(pd);
+    if (lane == 0) red_dyn[warp * LD + d] = pd;
+  }
+  __syncthreads();
+  for (int d = tid; d < LD; d += 128)
+    coldot_part[(size_t)blockIdx.x * LD + d] =
+        d < D ? (red_dyn[d] + red_dyn[LD + d]) + (red_dyn[2 * LD + d] + red_dyn[3 * LD + d]) : 0.f;
+}
+
+int prior_gemm_aug(const PriorWs& w, int B, int C, int D, cudaStream_t st) {
+  const long long total = (long long)(B + C) * w.KA;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  prior_aug_kernel<<<blocks, 256, 0, st>>>(w.zs, w.ms, w.nb2, B, C, D, w.LD, w.KA, w.zaug, w.maug);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EXVAE_OK : (int)e;
+}
+
+// S = Z'.M'^T with a prior epilogue
+int prior_gemm_logits(const PriorWs& w, int B, int C, int epi, const TcPriorEpi& pe, int* ntn, cudaStream_t st) {
+  TcGemm g{};
+  g.a = w.zaug; g.a_rows = B; g.a_cols = w.KA; g.a_mn = false;
+  g.b = w.maug; g.b_rows = C; g.b_cols = w.KA; g.b_mn = false;
+  g.M = B; g.N = C; g.K = w.KA; g.epi = epi; g.out0 = w.gpart; g.ldc = 4;
+  g.prior = pe;
+  if (ntn) *ntn = tc_gemm_ntn(g);
+  return tc_gemm_launch(g, st);
+}
+
 inline bool bwd_simt_forced() {
   static const bool forced = [] { const char* e = getenv("EXVAE_PRIOR_BWD"); return e && strcmp(e, "simt") == 0; }();
   return forced;
@@ -768,8 +910,8 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
                                    exvae_stream_t stream) {
   EXVAE_CHECK_ARG(z && mu && logvar && stats && ws);
   EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
-  if (D > 128) return EXVAE_ERR_UNSUPPORTED;
   const PriorWs w = prior_ws_layout(B, C, D, true, ws);
+  if (D > 128 && !w.gemm) return EXVAE_ERR_UNSUPPORTED;
   // fwd only touches the leading (fwd) part of the layout: accept a fwd-only sized workspace too
   const size_t need = prior_ws_layout(B, C, D, false, nullptr).bytes;
   if (ws_bytes < need) return EXVAE_ERR_WORKSPACE;
@@ -777,6 +919,21 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
   int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, st);
   if (rc) return rc;
   const bool mask = z_idx && mu_idx;
+  if (w.gemm) {
+    // D >= 64: the logit tile is a dense z.mu^T contraction -> persistent 3xTF32 tcgen05 GEMM, online LSE in its epilogue
+    rc = prior_gemm_aug(w, B, C, D, st);
+    if (rc) return rc;
+    TcPriorEpi pe{};
+    pe.cidx = mask ? reinterpret_cast<const long long*>(w.cidx) : nullptr;
+    pe.zidx = reinterpret_cast<const long long*>(z_idx);
+    pe.part = w.gpart;
+    int ntn = 0;
+    rc = prior_gemm_logits(w, B, C, TC_LSE, pe, &ntn, st);
+    if (rc) return rc;
+    lse_merge_kernel<false><<<ceil_div(B, 8), 256, 0, st>>>(w.gpart, ntn, (size_t)ntn * 4, 4, B, nullptr, nullptr, D, 0.f,
+                                                            stats, nullptr, nullptr);
+    EXVAE_RETURN_LAST_ERROR();
+  }
   if (w.KP && prior_tc_enabled()) {
     if (mask) {
       prior_mask_list_kernel<<<dim3(ceil_div(C, 256), ceil_div(B, 128)), 256, 0, st>>>(z_idx, mu_idx, B, C, w.mcnt,
@@ -825,8 +982,8 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
                                    size_t ws_bytes, int ws_prepared, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(z && mu && logvar && lse2 && grad_log_p && dz && dmu && dlogvar && ws);
   EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
-  if (D > 128) return EXVAE_ERR_UNSUPPORTED;
   const PriorWs w = prior_ws_layout(B, C, D, true, ws);
+  if (D > 128 && !w.gemm) return EXVAE_ERR_UNSUPPORTED;
   if (ws_bytes < w.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (!ws_prepared) {
@@ -834,6 +991,46 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
     if (rc) return rc;
   }
   const bool mask = z_idx && mu_idx;
+  if (w.gemm) {
+    int rc;
+    if (!ws_prepared) {
+      rc = prior_gemm_aug(w, B, C, D, st);
+      if (rc) return rc;
+    }
+    // W = g * 2^(S - lse2) (recomputed), stored as W [B][ldw] and W^T [C][ldwt]
+    TcPriorEpi pe{};
+    pe.cidx = mask ? reinterpret_cast<const long long*>(w.cidx) : nullptr;
+    pe.zidx = reinterpret_cast<const long long*>(z_idx);
+    pe.g = grad_log_p; pe.lse2 = lse2;
+    pe.w = w.wmat; pe.ldw = w.ldw; pe.wt = w.wtmat; pe.ldwt = w.ldwt;
+    rc = prior_gemm_logits(w, B, C, TC_PW, pe, nullptr, st);
+    if (rc) return rc;
+    {  // W.M' : reduction over the C exemplars, split into chains of <= 2560 (TMEM accumulation truncates)
+      TcGemm g{};
+      g.a = w.wtmat; g.a_rows = C; g.a_cols = w.ldwt; g.a_mn = true;
+      g.b = w.maug; g.b_rows = C; g.b_cols = w.KA; g.b_mn = true;
+      g.M = B; g.N = w.KA; g.K = C; g.epi = TC_SPLITK; g.out0 = w.p1; g.ldc = w.KA;
+      g.splits = w.S1; g.kchunk = w.kchunk1;
+      rc = tc_gemm_launch(g, st);
+      if (rc) return rc;
+    }
+    {  // W^T.Z' : reduction over the B latents
+      TcGemm g{};
+      g.a = w.wmat; g.a_rows = B; g.a_cols = w.ldw; g.a_mn = true;
+      g.b = w.zaug; g.b_rows = B; g.b_cols = w.KA; g.b_mn = true;
+      g.M = C; g.N = w.KA; g.K = B; g.epi = TC_SPLITK; g.out0 = w.p2; g.ldc = w.KA;
+      g.splits = w.S2; g.kchunk = w.kchunk2;
+      rc = tc_gemm_launch(g, st);
+      if (rc) return rc;
+    }
+    prior_gemm_rows_kernel<<<ceil_div(B, 8), 256, 0, st>>>(w.p1, w.S1, w.zs, w.isig, B, D, w.LD, w.KA, dz, w.rowdot, w.rs);
+    EXVAE_CUDA(cudaGetLastError());
+    const int ntile = ceil_div(C, 128);
+    prior_gemm_cols_kernel<<<ntile, 128, 4 * w.LD * sizeof(float), st>>>(w.p2, w.S2, w.ms, w.isig, C, D, w.LD, w.KA, dmu, w.coldot_part);
+    EXVAE_CUDA(cudaGetLastError());
+    prior_bwd_dlogvar_kernel<<<D, 256, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, ntile, D, w.LD, dlogvar);
+    EXVAE_RETURN_LAST_ERROR();
+  }
   if (w.NG && prior_tc_enabled() && !bwd_simt_forced()) {
     // tensor-core path: transposed operand planes + padded row arrays, two passes of prior_bwd_tc_kernel, then the
     // same row / dlogvar reductions as the FMA path (over nsplit partials instead of one per 64-column tile)
