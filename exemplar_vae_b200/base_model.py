@@ -71,7 +71,26 @@ def flat_chw(h):
     return h.reshape(N, -1) if C == 1 else h.permute(0, 3, 1, 2).reshape(N, -1)
 
 
+class PaddedBank(tuple):
+    """(centers [cap,D], log_variance, dataset indices [cap]) of the kNN mode with a FIXED capacity cap = B*k: the
+    number of selected exemplars is data dependent (torch.unique, models/BaseModel.py:265) and stays on the device
+    as ``count`` ([1] int32), so the whole step is graph-capturable; entries beyond ``count`` repeat entry 0 and are
+    ignored by the prior kernel."""
+
+    def __new__(cls, items, count):
+        self = super().__new__(cls, items)
+        self.count = count
+        return self
+
+    def valid(self):
+        """The reference's variable-length triple (one host sync)."""
+        n = int(self.count.item())
+        return tuple(t[:n] for t in self)
+
+
 class BaseModel(nn.Module, ABC):
+    knn_graph_capturable = True        # get_approximate_nearest_exemplars has no host sync
+
     def __init__(self, args):
         super().__init__()
         self.args = args
@@ -220,6 +239,8 @@ class BaseModel(nn.Module, ABC):
 
     def log_p_z_exemplar(self, z, z_indices, exemplars_embedding, test):
         """models/BaseModel.py:98-109 — the [B,C] matrix (materialising, no autograd)."""
+        if isinstance(exemplars_embedding, PaddedBank):          # materialising path: the reference's variable-length bank
+            exemplars_embedding = exemplars_embedding.valid()
         centers, center_log_variance, center_indices = exemplars_embedding
         lv = center_log_variance[0, :] if center_log_variance.dim() == 2 else center_log_variance
         masked = (test is False) and (self.args.no_mask is False)
@@ -319,7 +340,8 @@ class BaseModel(nn.Module, ABC):
             if c_total is not None and self.bank_group is not None:     # range-sharded bank (distributed.py)
                 return ops.prior_lse_sharded(z, centers, lv, z_indices if masked else None,
                                              center_indices if masked else None, c_total, self.bank_group)
-            return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None)
+            return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None,
+                                 c_valid=getattr(exemplars_embedding, "count", None))
         raise Exception('Wrong name of the prior!')
 
     # ------------------------------------------------------------------ generation helpers
@@ -459,13 +481,14 @@ class BaseModel(nn.Module, ABC):
         ops.scatter_rows_(cached_z, indices.reshape(-1), z.detach())
         sub_cache = ops.gather_rows(cached_z, exemplars_indices)
         nearest_indices, _ = ops.knn_topk(z.detach(), sub_cache, int(self.args.approximate_k))
-        uniq, count = ops.unique_positions(nearest_indices, sub_cache.shape[0])
-        nearest = uniq[:int(count.item())]            # data-dependent size: one host sync, like torch.unique
-        exemplars_indices = exemplars_indices[nearest].view(-1)
+        # torch.unique (BaseModel.py:265) has a data-dependent size: keep the fixed upper bound B*k and a device-side
+        # count instead (no host sync, so the step can be captured in a CUDA graph); the tail repeats entry 0
+        nearest, count = ops.unique_positions(nearest_indices, sub_cache.shape[0])
+        exemplars_indices = ops.gather_index(exemplars_indices, nearest)
         exemplars = ops.gather_rows(self.resident(dataset), exemplars_indices)
         exemplars_z, log_variance = self.q_z(exemplars, prior=True)
         ops.scatter_rows_(cached_z, exemplars_indices, exemplars_z.detach())
-        return (exemplars_z, log_variance, exemplars_indices)
+        return PaddedBank((exemplars_z, log_variance, exemplars_indices), count)
 
 
 class AbsModel(BaseModel):

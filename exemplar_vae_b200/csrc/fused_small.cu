@@ -69,6 +69,11 @@ __global__ void __launch_bounds__(256) reparam_logq_bwd_kernel(const float* __re
   }
 }
 
+__global__ void __launch_bounds__(256) gather_index_kernel(const long long* __restrict__ src, const long long* __restrict__ idx,
+                                                           int n, long long* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = src[idx[i]];
+}
+
 __global__ void __launch_bounds__(256) concat_cols_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                               long long R, int Ka, int Kb, float* __restrict__ out) {
   const int K = Ka + Kb;
@@ -131,6 +136,14 @@ extern "C" int exvae_reparam_logq_bwd(const float* mu, const float* logvar, cons
   EXVAE_CHECK_ARG(mu && logvar && eps && z && B > 0 && D > 0 && (dmu || dlogvar));
   const long long n = (long long)B * D;
   reparam_logq_bwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(mu, logvar, eps, z, dz, dlogq, n, D, dmu, dlogvar);
+  EXVAE_RETURN_LAST_ERROR();
+}
+
+extern "C" int exvae_gather_index(const int64_t* src, const int64_t* idx, int n, int64_t* out, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(src && idx && out && n > 0);
+  gather_index_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(src),
+                                                                   reinterpret_cast<const long long*>(idx), n,
+                                                                   reinterpret_cast<long long*>(out));
   EXVAE_RETURN_LAST_ERROR();
 }
 

@@ -3,8 +3,7 @@
 //   pairwise_distance                 utils/distributions.py:12-18   (fp64 inside, fp32 out)
 //   log_normal_diag_vectorized        utils/distributions.py:21-25
 //   log_p_z_exemplar, sum=False       models/BaseModel.py:98-109
-//   pairwise_distance(...).topk(k, largest=False)   models/BaseModel.py:263-264
-//   find_nearest_neighbors            utils/knn_on_latent.py:4-9
+//   (the fused distance + top-k selection of models/BaseModel.py:263-264 / utils/knn_on_latent.py:4-9 is knn_fused.cu)
 //   torch.unique(nearest)             models/BaseModel.py:265
 //
 // The reference computes ||z||^2 + ||mu||^2 - 2 z.mu in fp64 and rounds to fp32 BEFORE the
@@ -169,65 +168,6 @@ struct Cand {
 __device__ __forceinline__ bool cand_less(float v, int i, float bv, int bi) { return v < bv || (v == bv && i < bi); }
 __device__ __forceinline__ Cand cand_min(Cand a, Cand b) { return cand_less(b.v, b.i, a.v, a.i) ? b : a; }
 
-// One CTA per row.  Pass p selects the lexicographically smallest (value, position) strictly
-// greater than the (p-1)-th selection: no marking, duplicates handled, deterministic.
-// The row is staged in shared memory when it fits (`smem_cols` >= C), else re-read through L2.
-__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ dist, int C, int k,
-                                                        int64_t pos_offset, int smem_cols,
-                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_dist) {
-  extern __shared__ float row_s[];
-  __shared__ Cand wbest[8];
-  __shared__ Cand chosen;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
-  const float* src = dist + (size_t)b * C;
-  const bool staged = smem_cols >= C;
-  if (staged) {
-    for (int c = tid; c < C; c += 256) row_s[c] = src[c];
-    __syncthreads();
-  }
-  const float* row = staged ? row_s : src;
-  float lv = -INFINITY;
-  int li = -1;
-  for (int p = 0; p < k; ++p) {
-    Cand best{INFINITY, 0x7fffffff};
-    for (int c = tid; c < C; c += 256) {
-      const float v = row[c];
-      const bool after = (v > lv) || (v == lv && c > li);
-      if (after && cand_less(v, c, best.v, best.i)) best = Cand{v, c};
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      Cand other;
-      other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-      other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-      best = cand_min(best, other);
-    }
-    if (lane == 0) wbest[warp] = best;
-    __syncthreads();
-    if (tid == 0) {
-      Cand c0 = wbest[0];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) c0 = cand_min(c0, wbest[w]);
-      chosen = c0;
-      const bool found = c0.i != 0x7fffffff;
-      out_idx[(size_t)b * k + p] = found ? (int64_t)c0.i + pos_offset : (int64_t)-1;
-      out_dist[(size_t)b * k + p] = found ? c0.v : INFINITY;
-    }
-    __syncthreads();
-    lv = chosen.v;
-    li = chosen.i;
-    if (li == 0x7fffffff) {  // fewer than k candidates: fill the tail
-      if (tid == 0)
-        for (int q = p + 1; q < k; ++q) {
-          out_idx[(size_t)b * k + q] = -1;
-          out_dist[(size_t)b * k + q] = INFINITY;
-        }
-      break;
-    }
-  }
-}
-
 // Merge G per-shard lists: one warp per row over G*k candidates keyed by (dist, global position).
 __global__ void __launch_bounds__(256) knn_merge_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dist,
                                                         int G, int B, int k, int64_t* __restrict__ out_idx,
@@ -313,6 +253,11 @@ __global__ void __launch_bounds__(1024) unique_positions_kernel(const int64_t* _
   for (int i = lo; i < hi; ++i)
     if (flags[i]) out[w++] = i;
   if (tid == 0) *out_count = s_total;
+  // fixed-size result (graph-capturable kNN mode): the tail [count, n) repeats the first selected position, so
+  // every entry is a valid row to gather / encode; consumers ignore it through the device-side count
+  __syncthreads();
+  const long long first = s_total > 0 ? out[0] : 0;
+  for (int i = s_total + tid; i < n; i += 1024) out[i] = first;
 }
 
 // ------------------------------------------------------------------------------ row movement
@@ -390,33 +335,6 @@ extern "C" int exvae_prior_logprob_matrix(const float* z, const float* mu, const
   }
   return launch_pairdist<PD_EXEMPLAR>(z, mu, logvar, mask ? z_idx : nullptr, mask ? mu_idx : nullptr,
                                       mask ? row_counts : nullptr, B, C, D, out, nullptr, st);
-}
-
-extern "C" size_t exvae_knn_workspace_bytes(int B, int C, int D, int k) {
-  (void)D;
-  (void)k;
-  if (B <= 0 || C <= 0) return 0;
-  return align_up(sizeof(float) * (size_t)B * C, 256);
-}
-
-extern "C" int exvae_knn_topk(const float* z, const float* bank, int B, int C, int D, int k, int metric,
-                              int64_t pos_offset, int64_t* out_idx, float* out_dist, void* ws, size_t ws_bytes,
-                              exvae_stream_t stream) {
-  EXVAE_CHECK_ARG(z && bank && out_idx && out_dist && ws && B > 0 && C > 0 && D > 0 && k > 0);
-  EXVAE_CHECK_ARG(metric == 0 || metric == 1);
-  if (ws_bytes < exvae_knn_workspace_bytes(B, C, D, k)) return EXVAE_ERR_WORKSPACE;
-  cudaStream_t st = as_stream(stream);
-  float* dist = static_cast<float*>(ws);
-  int rc = metric == 0 ? launch_pairdist<PD_PLAIN>(z, bank, nullptr, nullptr, nullptr, nullptr, B, C, D, dist, nullptr, st)
-                       : launch_pairdist<PD_EUCLID32>(z, bank, nullptr, nullptr, nullptr, nullptr, B, C, D, dist,
-                                                      nullptr, st);
-  if (rc) return rc;
-  const int max_cols = 200 * 1024 / 4;
-  const int smem_cols = C <= max_cols ? C : 0;
-  const size_t smem = (size_t)smem_cols * 4;
-  EXVAE_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  topk_rows_kernel<<<B, 256, smem, st>>>(dist, C, k, pos_offset, smem_cols, out_idx, out_dist);
-  EXVAE_RETURN_LAST_ERROR();
 }
 
 extern "C" int exvae_knn_merge(const int64_t* idx, const float* dist, int G, int B, int k, int64_t* out_idx,

@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restric
                                                           float* __restrict__ hz, float* __restrict__ ms,
                                                           float* __restrict__ nb2, int64_t* __restrict__ cidx,
                                                           float* __restrict__ isig, int KP, float* __restrict__ zp,
-                                                          float* __restrict__ mp, int* __restrict__ mcnt) {
+                                                          float* __restrict__ mp, int* __restrict__ mcnt,
+                                                          const int* __restrict__ c_valid) {
+  if (c_valid) C = min(C, max(*c_valid, 0));      // kNN mode: only the first *c_valid bank rows count
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (blockIdx.x == 0)
@@ -245,7 +247,9 @@ __global__ void __launch_bounds__(256) prior_stage_kernel(const float* __restric
 // masked-pair list for the tensor-core path: mcnt[b] = #{n : mu_idx[n] == z_idx[b]}, first PR_MAXM positions
 __global__ void __launch_bounds__(256) prior_mask_list_kernel(const int64_t* __restrict__ z_idx,
                                                               const int64_t* __restrict__ mu_idx, int B, int C,
-                                                              int* __restrict__ mcnt, int* __restrict__ mlist) {
+                                                              int* __restrict__ mcnt, int* __restrict__ mlist,
+                                                              const int* __restrict__ c_valid) {
+  if (c_valid) C = min(C, max(*c_valid, 0));
   // grid = (column chunks of 256, row chunks of 128): every thread compares its column with 128 rows
   __shared__ long long zs_idx[128];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -452,7 +456,8 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
                                                         size_t part_stride, int B, const float* __restrict__ z,
                                                         const float* __restrict__ logvar, int D, float c_total,
                                                         float* __restrict__ out_stats, float* __restrict__ log_p,
-                                                        float* __restrict__ lse2) {
+                                                        float* __restrict__ lse2, const int* __restrict__ c_valid = nullptr) {
+  if (FINAL && c_valid) c_total = (float)*c_valid;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -787,7 +792,7 @@ __global__ void __launch_bounds__(256) prior_aug_kernel(const float* __restrict_
     if (r < C) {
       float v = 0.f;
       if (k < D) v = ms[(size_t)r * LD + k];
-      else if (k == D) v = nb2[r];
+      else if (k == D) v = fmaxf(nb2[r], -1e30f);     // rows beyond the valid count carry -inf: keep the tf32 split finite
       else if (k == D + 1) v = 1.f;
       maug[e] = v;
     } else {
@@ -881,11 +886,11 @@ inline bool bwd_simt_forced() {
 }
 
 int stage(const PriorWs& w, const float* z, const float* mu, const float* logvar, const int64_t* mu_idx, int B, int C,
-          int D, cudaStream_t st) {
+          int D, const int* c_valid, cudaStream_t st) {
   const int rows = w.Cpad + w.Bpad;
   prior_stage_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, mu, logvar, mu_idx, B, C, D, w.LD, w.Bpad, w.Cpad, w.zs,
                                                         w.hz, w.ms, w.nb2, w.cidx, w.isig, w.KP, w.zp, w.mp,
-                                                        w.mcnt);
+                                                        w.mcnt, c_valid);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
@@ -906,8 +911,8 @@ extern "C" size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D) {
 }
 
 extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
-                                   const int64_t* mu_idx, int B, int C, int D, float* stats, void* ws, size_t ws_bytes,
-                                   exvae_stream_t stream) {
+                                   const int64_t* mu_idx, int B, int C, int D, const int* c_valid, float* stats, void* ws,
+                                   size_t ws_bytes, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(z && mu && logvar && stats && ws);
   EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
   const PriorWs w = prior_ws_layout(B, C, D, true, ws);
@@ -916,7 +921,7 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
   const size_t need = prior_ws_layout(B, C, D, false, nullptr).bytes;
   if (ws_bytes < need) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, st);
+  int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, c_valid, st);
   if (rc) return rc;
   const bool mask = z_idx && mu_idx;
   if (w.gemm) {
@@ -937,7 +942,7 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
   if (w.KP && prior_tc_enabled()) {
     if (mask) {
       prior_mask_list_kernel<<<dim3(ceil_div(C, 256), ceil_div(B, 128)), 256, 0, st>>>(z_idx, mu_idx, B, C, w.mcnt,
-                                                                                        w.mlist);
+                                                                                        w.mlist, c_valid);
       EXVAE_CUDA(cudaGetLastError());
     }
     PriorTcArgs a{};
@@ -968,18 +973,19 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
 }
 
 extern "C" int exvae_prior_lse_finalize(const float* stats, int G, const float* z, const float* logvar, int B, int D,
-                                        int64_t C_total, float* log_p, float* lse2, exvae_stream_t stream) {
+                                        int64_t C_total, const int* c_valid, float* log_p, float* lse2,
+                                        exvae_stream_t stream) {
   EXVAE_CHECK_ARG(stats && z && logvar && log_p && lse2);
   EXVAE_CHECK_ARG(G > 0 && B > 0 && D > 0 && C_total > 0);
   lse_merge_kernel<true><<<ceil_div(B, 8), 256, 0, as_stream(stream)>>>(stats, G, 4, (size_t)B * 4, B, z, logvar, D,
-                                                                        (float)C_total, nullptr, log_p, lse2);
+                                                                        (float)C_total, nullptr, log_p, lse2, c_valid);
   EXVAE_RETURN_LAST_ERROR();
 }
 
 extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
                                    const int64_t* mu_idx, int B, int C, int D, const float* lse2,
                                    const float* grad_log_p, float* dz, float* dmu, float* dlogvar, void* ws,
-                                   size_t ws_bytes, int ws_prepared, exvae_stream_t stream) {
+                                   size_t ws_bytes, int ws_prepared, const int* c_valid, exvae_stream_t stream) {
   EXVAE_CHECK_ARG(z && mu && logvar && lse2 && grad_log_p && dz && dmu && dlogvar && ws);
   EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
   const PriorWs w = prior_ws_layout(B, C, D, true, ws);
@@ -987,7 +993,7 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
   if (ws_bytes < w.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (!ws_prepared) {
-    int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, st);
+    int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, c_valid, st);
     if (rc) return rc;
   }
   const bool mask = z_idx && mu_idx;

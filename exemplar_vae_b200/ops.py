@@ -77,12 +77,14 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 # ======================================================================================
 class _PriorLSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group):
+    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group, c_valid):
         L = lib()
         z, mu, logvar = _f32(z, "z"), _f32(mu, "mu"), _f32(logvar, "logvar")
         B, D = z.shape
         C = mu.shape[0]
         assert mu.shape[1] == D and logvar.numel() == D
+        if c_valid is not None:
+            assert c_valid.is_cuda and c_valid.dtype == torch.int32 and c_valid.numel() == 1 and group is None
         z_idx = _i64(z_idx)
         mu_idx = _i64(mu_idx)
         if z_idx is not None:
@@ -95,8 +97,8 @@ class _PriorLSE(torch.autograd.Function):
         ws = _ws(L.exvae_prior_lse_workspace_bytes(B, C, D) if need_bwd else
                  L.exvae_prior_lse_fwd_workspace_bytes(B, C, D), z.device)
         stats = torch.empty((B, 4), dtype=torch.float32, device=z.device)
-        L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(stats), _p(ws),
-                                      ws.numel(), _stream()), "prior_lse_fwd")
+        L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(c_valid), _p(stats),
+                                      _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
         _count(4 if (z_idx is not None and mu_idx is not None) else 3)   # stage, [mask list], main, merge
         G = 1
         all_stats = stats
@@ -108,36 +110,39 @@ class _PriorLSE(torch.autograd.Function):
         total = int(c_total) if c_total is not None else C
         log_p = torch.empty((B,), dtype=torch.float32, device=z.device)
         lse2 = torch.empty((B,), dtype=torch.float32, device=z.device)
-        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z), _p(logvar), B, D, total, _p(log_p), _p(lse2),
-                                           _stream()), "prior_lse_finalize")
+        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z), _p(logvar), B, D, total, _p(c_valid), _p(log_p),
+                                           _p(lse2), _stream()), "prior_lse_finalize")
         _count(1)
-        ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws)
+        ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid)
         ctx.dims = (B, C, D)
         return log_p
 
     @staticmethod
     def backward(ctx, g):
         L = lib()
-        z, mu, logvar, z_idx, mu_idx, lse2, ws = ctx.saved_tensors
+        z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid = ctx.saved_tensors
         B, C, D = ctx.dims
         g = _f32(g, "grad")
         dz = torch.empty_like(z)
         dmu = torch.empty_like(mu)
         dlv = torch.empty((D,), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_bwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(lse2), _p(g),
-                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _stream()), "prior_lse_bwd")
-        _count(5 if D <= 63 else 3)   # tensor-core path: prep, two passes, rows, dlogvar; FMA path: main, rows, dlogvar
-        return dz, dmu, dlv.view_as(logvar), None, None, None, None
+                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _p(c_valid), _stream()),
+                "prior_lse_bwd")
+        _count(5 if D <= 63 else 6)   # D <= 63: prep, two passes, rows, dlogvar; D >= 64: W pass, two GEMMs, rows, cols, dlogvar
+        return dz, dmu, dlv.view_as(logvar), None, None, None, None, None
 
 
-def prior_lse(z, mu, logvar, z_idx=None, mu_idx=None, c_total=None, group=None) -> torch.Tensor:
+def prior_lse(z, mu, logvar, z_idx=None, mu_idx=None, c_total=None, group=None, c_valid=None) -> torch.Tensor:
     """log p(z_b) = LSE_n log N(z_b | mu_n, exp(logvar)) - log(C - #masked_b)   -> [B].
 
     ``logvar`` is the [D] log-variance vector shared by all exemplars.  ``z_idx``/``mu_idx``
     enable the leave-one-out mask.  With ``group`` the bank ``mu`` is this rank's shard of a
     range-sharded bank: partial (max, sum, count) statistics are all-gathered once and merged;
-    ``c_total`` is the global exemplar count.  dz/dlogvar gradients are then per-shard partials."""
-    return _PriorLSE.apply(z, mu, logvar, z_idx, mu_idx, c_total, group)
+    ``c_total`` is the global exemplar count.  dz/dlogvar gradients are then per-shard partials.
+    ``c_valid`` ([1] int32 on the device): only the first ``c_valid`` bank rows count (fixed-capacity bank of the
+    kNN mode); the normaliser then uses that count."""
+    return _PriorLSE.apply(z, mu, logvar, z_idx, mu_idx, c_total, group, c_valid)
 
 
 # ======================================================================================
@@ -254,7 +259,7 @@ def knn_topk(z, bank, k: int, metric: int = 0, pos_offset: int = 0):
     ws = _ws(L.exvae_knn_workspace_bytes(B, C, D, k), z.device)
     L.check(L.exvae_knn_topk(_p(z), _p(bank), B, C, D, k, metric, pos_offset, _p(idx), _p(dist), _p(ws), ws.numel(),
                              _stream()), "knn_topk")
-    _count(2)
+    _count(1)
     return idx, dist
 
 
@@ -298,6 +303,18 @@ def gather_rows(src, idx, out=None) -> torch.Tensor:
     assert out.is_contiguous() and tuple(out.shape) == (n, row) and out.dtype == torch.float32
     if n:
         L.check(L.exvae_gather_rows(_p(src), _p(idx), n, row, _p(out), _stream()), "gather_rows")
+        _count(1)
+    return out
+
+
+@torch.no_grad()
+def gather_index(src, idx) -> torch.Tensor:
+    """src[idx] for int64 vectors (exemplars_indices[nearest], models/BaseModel.py:266)."""
+    L = lib()
+    src, idx = _i64(src).reshape(-1), _i64(idx).reshape(-1)
+    out = torch.empty_like(idx)
+    if idx.numel():
+        L.check(L.exvae_gather_index(_p(src), _p(idx), idx.numel(), _p(out), _stream()), "gather_index")
         _count(1)
     return out
 
@@ -998,14 +1015,14 @@ class _PriorLSESharded(torch.autograd.Function):
         Bt = G * B
         ws = _ws(L.exvae_prior_lse_workspace_bytes(Bt, C, D), z.device)
         stats = torch.empty((Bt, 4), dtype=torch.float32, device=z.device)
-        L.check(L.exvae_prior_lse_fwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(stats),
+        L.check(L.exvae_prior_lse_fwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, None, _p(stats),
                                       _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
         _count(3)
         all_stats = torch.empty((G, Bt, 4), dtype=torch.float32, device=z.device)
         dist.all_gather_into_tensor(all_stats, stats, group=group)
         log_p = torch.empty((Bt,), dtype=torch.float32, device=z.device)
         lse2 = torch.empty((Bt,), dtype=torch.float32, device=z.device)
-        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z_all), _p(logvar), Bt, D, int(c_total), _p(log_p),
+        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z_all), _p(logvar), Bt, D, int(c_total), None, _p(log_p),
                                            _p(lse2), _stream()), "prior_lse_finalize")
         _count(1)
         ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws)
@@ -1025,7 +1042,7 @@ class _PriorLSESharded(torch.autograd.Function):
         dmu = torch.empty_like(mu)
         dlv = torch.empty((D,), dtype=torch.float32, device=g.device)
         L.check(L.exvae_prior_lse_bwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(lse2),
-                                      _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _stream()),
+                                      _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, None, _stream()),
                 "prior_lse_bwd")
         _count(3)
         dz = torch.empty((B, D), dtype=torch.float32, device=g.device)

@@ -68,20 +68,27 @@ EXVAE_API int exvae_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * and lse2[b] (base-2 row log-sum, saved for the backward).
  * bwd: given dL/dlog_p returns dz [B,D] (partial over this shard), dmu [C,D] (complete for
  * this shard) and dlogvar [D] (partial over this shard).
+ * c_valid (nullable device int32): only the first *c_valid rows of the bank count (the kNN mode selects a
+ * data-dependent number of exemplars, models/BaseModel.py:265-266; the bank is then a fixed-capacity [C,D] buffer and
+ * the count stays on the device, so the step is graph-capturable).  Rows beyond it contribute nothing (their dmu is
+ * 0) and finalize uses *c_valid as the normaliser's exemplar count.
+ * D <= 63: dedicated tcgen05 kernels (prior_lse_tc.cu / prior_bwd_tc.cu); D >= 64: the logit tile is a dense
+ * z.mu^T contraction and runs through the persistent 3xTF32 tcgen05 GEMM with LSE / weight epilogues (gemm_tc.cu).
  */
 EXVAE_API size_t exvae_prior_lse_workspace_bytes(int B, int C, int D);     /* forward + backward */
 EXVAE_API size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D); /* forward only (evaluation) */
 EXVAE_API int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
-                        const int64_t* mu_idx, int B, int C, int D, float* stats /*[B,4]*/, void* ws,
+                        const int64_t* mu_idx, int B, int C, int D, const int* c_valid, float* stats /*[B,4]*/, void* ws,
                         size_t ws_bytes, exvae_stream_t stream);
 EXVAE_API int exvae_prior_lse_finalize(const float* stats /*[G,B,4]*/, int G, const float* z, const float* logvar, int B, int D,
-                             int64_t C_total, float* log_p /*[B]*/, float* lse2 /*[B]*/, exvae_stream_t stream);
+                             int64_t C_total, const int* c_valid, float* log_p /*[B]*/, float* lse2 /*[B]*/,
+                             exvae_stream_t stream);
 /* ws must be the workspace a fwd call with the same arguments filled (ws_prepared=1) or any
  * workspace of the right size (ws_prepared=0: the bank is re-staged). */
 EXVAE_API int exvae_prior_lse_bwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
                         const int64_t* mu_idx, int B, int C, int D, const float* lse2, const float* grad_log_p,
                         float* dz, float* dmu, float* dlogvar, void* ws, size_t ws_bytes, int ws_prepared,
-                        exvae_stream_t stream);
+                        const int* c_valid, exvae_stream_t stream);
 
 /* ---------------------------------------------------------------- materialising primitives
  * pairwise_distance (utils/distributions.py:12-18): fp64 inside, fp32 [B,C] out.            */
@@ -114,7 +121,9 @@ EXVAE_API int exvae_vamp_lse_bwd(const float* z, const float* mean, const float*
  * pairwise_distance(z, bank).topk(k, largest=False) (models/BaseModel.py:263-264): fp64
  * expansion distance rounded to fp32, k smallest per row sorted ascending, ties -> lowest
  * position.  metric 1 = direct-difference fp32 Euclidean with sqrt (utils/knn_on_latent.py:4-9).
- * pos_offset is added to every returned position (bank shards).                                */
+ * pos_offset is added to every returned position (bank shards).  ONE kernel (knn_fused.cu): distance tiles and a
+ * per-row running top-k (k <= 32) stay on chip, the [B,C] matrix is never written; >= 148 CTAs by splitting the
+ * bank columns, merged by the last CTA of each row block.                                          */
 EXVAE_API size_t exvae_knn_workspace_bytes(int B, int C, int D, int k);
 EXVAE_API int exvae_knn_topk(const float* z, const float* bank, int B, int C, int D, int k, int metric, int64_t pos_offset,
                    int64_t* out_idx /*[B,k]*/, float* out_dist /*[B,k]*/, void* ws, size_t ws_bytes,
@@ -123,8 +132,8 @@ EXVAE_API int exvae_knn_topk(const float* z, const float* bank, int B, int C, in
 EXVAE_API int exvae_knn_merge(const int64_t* idx, const float* dist, int G, int B, int k, int64_t* out_idx, float* out_dist,
                     exvae_stream_t stream);
 /* torch.unique(positions) (models/BaseModel.py:265) for positions in [0, range): ascending unique
- * values in out[0..count) (capacity n), count written to *out_count (device int32).
- * flags: scratch [range] int32.                                                                  */
+ * values in out[0..count) (capacity n), count written to *out_count (device int32); out[count..n) repeats
+ * out[0] so that the fixed-capacity result only holds valid positions.  flags: scratch [range] int32.   */
 EXVAE_API int exvae_unique_positions(const int64_t* pos, int n, int range, int64_t* out, int* out_count, int* flags,
                            exvae_stream_t stream);
 
@@ -213,6 +222,8 @@ EXVAE_API int exvae_concat_cols_fwd(const float* a, const float* b, int64_t R, i
                                     exvae_stream_t stream);
 EXVAE_API int exvae_concat_cols_bwd(const float* dout, int64_t R, int Ka, int Kb, float* da, float* db,
                                     exvae_stream_t stream);
+/* out[i] = src[idx[i]] for int64 vectors: exemplars_indices[nearest] (models/BaseModel.py:266) */
+EXVAE_API int exvae_gather_index(const int64_t* src, const int64_t* idx, int n, int64_t* out, exvae_stream_t stream);
 /* zero `bytes` bytes (cudaMemsetAsync): the one gradient-buffer reset of a training step. */
 EXVAE_API int exvae_zero(void* ptr, size_t bytes, exvae_stream_t stream);
 /* log_normal_diag(x, mean, log_var, dim=1) (utils/distributions.py:28-33): out [B]. */

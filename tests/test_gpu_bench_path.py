@@ -136,3 +136,44 @@ def test_iwae_prior_shape_vs_fp64_oracle():
     rows = np.arange(0, B, 37)
     ref = O.log_p_z_exemplar_lse_f64(z[rows].numpy(), None, mu.numpy(), lv.numpy(), None, masked=False)
     close(lp[rows], ref, rtol=1e-4)
+
+
+def test_knn_mode_step_is_graph_capturable_and_matches_eager():
+    """BASELINE configs[2] path (approximate_prior, kNN cache): the selection keeps a fixed capacity B*k and a device
+    count (no host sync), so the whole step replays from a CUDA graph; replay == eager, incl. the refreshed cache."""
+    import exemplar_vae_b200 as E
+    T, N, B, k, D = 4000, 2000, 100, 10, 40
+    args = O.make_args(model_name="vae", hidden_size=300, number_components=N, training_set_size=T, device="cuda",
+                       approximate_prior=True, approximate_k=k)
+    args.dynamic_binarization = False
+    p0 = O.init_params(args, seed=5)
+    data = O.synthetic_dataset(T)
+    dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
+    gen = torch.Generator().manual_seed(77)
+    draws = []
+    for _ in range(3):
+        bidx = torch.randperm(T, generator=gen)[:B]
+        draws.append((bidx, torch.bernoulli(data[bidx], generator=gen), torch.randint(0, T, (N,), generator=gen),
+                      torch.randn(B, D, generator=gen)))
+    results = []
+    for use_graph in (False, True):
+        m = _fresh(args, p0)
+        assert m.knn_graph_capturable
+        opt = E.AdamNormGrad(m.parameters(), lr=LR)
+        with torch.no_grad():
+            cache = m.cache_z(dataset)
+        cache = (cache[0].contiguous().clone(), cache[1].contiguous().clone())
+        static = {"eps": [torch.zeros(B, D, device="cuda")], "exemplar_indices": torch.zeros(N, dtype=torch.int64, device="cuda")}
+        step = E.GraphedTrainStep(m, opt, args, dataset, B, beta=1.0, warmup_steps=2, use_graph=use_graph,
+                                  rng_override=static, cache=cache)
+        assert (step.graph is not None) == use_graph
+        losses = []
+        for bidx, x, ex_idx, eps in draws:
+            static["eps"][0].copy_(eps)
+            static["exemplar_indices"].copy_(ex_idx)
+            losses.append(step.step(x.cuda(), bidx.cuda()).clone())
+        results.append((torch.stack(losses).cpu(), cache[0].cpu(), {k_: v.detach().cpu() for k_, v in m.state_dict().items()}))
+    (l0, c0, s0), (l1, c1, s1) = results
+    close(l1, l0, rtol=1e-5)
+    close(c1, c0, rtol=1e-4, atol=1e-5)
+    _params_agree(s1, s0, 3, "knn graph vs eager")

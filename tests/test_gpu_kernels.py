@@ -283,6 +283,59 @@ def test_knn_topk_cfg3_size_vs_oracle(ops):
     assert np.array_equal(mi.cpu().numpy(), idx_ref)
 
 
+@pytest.mark.parametrize("B,C,D,k,metric", [(7, 33, 5, 32, 0), (130, 1000, 128, 20, 1), (65, 10, 8, 16, 0),
+                                            (300, 70000, 16, 5, 0), (64, 64, 40, 1, 0), (100, 100000, 128, 10, 0)])
+def test_knn_fused_shapes_vs_oracle(ops, B, C, D, k, metric):
+    """The fused distance + running top-k kernel at ragged / edge geometries: k = 32 (one list entry per lane), fewer
+    candidates than k (tail = -1), several row blocks, many column splits, cfg5's N=100 000 x D=128 cache."""
+    rng = np.random.default_rng(B + C + k)
+    bank = rng.normal(size=(C, D)).astype(np.float32)
+    z = (bank[rng.integers(0, C, size=B)] + 0.3 * rng.normal(size=(B, D))).astype(np.float32)
+    idx, dist = ops.knn_topk(dev(z), dev(bank), k, metric=metric)
+    idx = idx.cpu().numpy()
+    kk = min(k, C)
+    if metric == 0:
+        _, ref = O.nearest_exemplar_positions_np(z, bank, kk)
+    else:
+        ref = O.find_nearest_neighbors_np(z, bank, kk)
+    assert np.array_equal(idx[:, :kk], ref)
+    assert (idx[:, kk:] == -1).all()
+    # the unique of a fixed-capacity result: valid head, tail repeats the first entry
+    uniq, count = ops.unique_positions(torch.as_tensor(idx[:, :kk]).cuda(), C)
+    n = int(count.item())
+    u = uniq.cpu().numpy()
+    assert np.array_equal(u[:n], np.unique(ref.reshape(-1))) and (u[n:] == u[0]).all()
+
+
+def test_prior_lse_valid_count(ops):
+    """kNN mode keeps a fixed-capacity bank and a device-side count: rows beyond the count must not contribute to
+    log p(z) (incl. the normaliser, models/BaseModel.py:107-108) nor receive / produce gradient."""
+    g = torch.Generator().manual_seed(3)
+    for B, cap, n, D in ((100, 1000, 983, 40), (64, 640, 300, 128)):
+        mu = torch.randn(cap, D, generator=g)
+        lv = torch.full((D,), -2.0)
+        src = torch.randint(0, n, (B,), generator=g)
+        z = mu[src] + torch.exp(0.5 * lv) * torch.randn(B, D, generator=g)
+        mu_idx = torch.randperm(50000, generator=g)[:cap]
+        z_idx = mu_idx[src].clone()
+        gout = torch.randn(B, generator=g)
+        cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+        outs = []
+        for full in (False, True):
+            zc, lc = z.cuda().requires_grad_(True), lv.cuda().requires_grad_(True)
+            mc = (mu.cuda() if full else mu[:n].cuda()).requires_grad_(True)
+            mi = mu_idx.cuda() if full else mu_idx[:n].cuda()
+            lp = ops.prior_lse(zc, mc, lc, z_idx.cuda(), mi, c_valid=cnt if full else None)
+            lp.backward(gout.cuda())
+            outs.append((lp.detach(), zc.grad, mc.grad, lc.grad))
+        (lp0, dz0, dm0, dl0), (lp1, dz1, dm1, dl1) = outs
+        close(lp1, lp0, rtol=1e-6)
+        close(dz1, dz0, rtol=1e-5, atol=1e-6 * float(dz0.abs().max()))
+        close(dm1[:n], dm0, rtol=1e-5, atol=1e-6 * float(dm0.abs().max()))
+        assert float(dm1[n:].abs().max()) == 0.0
+        close(dl1, dl0, rtol=1e-4, atol=1e-5 * float(dl0.abs().max()))
+
+
 def test_gather_scatter_rows(ops):
     src = torch.randn(1000, 784, device="cuda")
     idx = torch.randint(0, 1000, (333,), device="cuda")

@@ -127,6 +127,8 @@ def test_approximate_prior_golden(golden):
     with torch.no_grad():
         zm, zl = model.q_z(x)
         sel = model.get_approximate_nearest_exemplars((zm, zl, xi), cache2, dataset)
+    assert sel[2].numel() == x.shape[0] * int(g["k"])         # fixed capacity B*k, count on the device
+    sel = sel.valid()
     assert np.array_equal(sel[2].cpu().numpy(), g["sel_indices"])
     close(sel[0], g["sel_mean"], rtol=1e-4, atol=1e-5)
 
