@@ -74,17 +74,17 @@ def flat_chw(h):
 class PaddedBank(tuple):
     """(centers [cap,D], log_variance, dataset indices [cap]) of the kNN mode with a FIXED capacity cap = B*k: the
     number of selected exemplars is data dependent (torch.unique, models/BaseModel.py:265) and stays on the device
-    as ``count`` ([1] int32), so the whole step is graph-capturable; entries beyond ``count`` repeat entry 0 and are
+    as ``valid_count`` ([1] int32), so the whole step is graph-capturable; entries beyond ``valid_count`` repeat entry 0 and are
     ignored by the prior kernel."""
 
     def __new__(cls, items, count):
         self = super().__new__(cls, items)
-        self.count = count
+        self.valid_count = count
         return self
 
     def valid(self):
         """The reference's variable-length triple (one host sync)."""
-        n = int(self.count.item())
+        n = int(self.valid_count.item())
         return tuple(t[:n] for t in self)
 
 
@@ -341,7 +341,7 @@ class BaseModel(nn.Module, ABC):
                 return ops.prior_lse_sharded(z, centers, lv, z_indices if masked else None,
                                              center_indices if masked else None, c_total, self.bank_group)
             return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None,
-                                 c_valid=getattr(exemplars_embedding, "count", None))
+                                 c_valid=getattr(exemplars_embedding, "valid_count", None))
         raise Exception('Wrong name of the prior!')
 
     # ------------------------------------------------------------------ generation helpers
