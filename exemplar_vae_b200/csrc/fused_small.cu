@@ -69,6 +69,44 @@ __global__ void __launch_bounds__(256) reparam_logq_bwd_kernel(const float* __re
   }
 }
 
+// one warp per row
+__global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, int R,
+                                                              int K, float* __restrict__ w) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float ss = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float x = v[(size_t)r * K + k];
+    ss = fmaf(x, x, ss);
+  }
+  ss = warp_sum(ss);
+  const float sc = g[r] / sqrtf(ss);
+  for (int k = lane; k < K; k += 32) w[(size_t)r * K + k] = v[(size_t)r * K + k] * sc;
+}
+// w = g v / n,  n = ||v||:   dg = <dw, v> / n ;  dv = (g / n) (dw - v <dw, v> / n^2)
+__global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                              const float* __restrict__ dw, int R, int K,
+                                                              float* __restrict__ dv, float* __restrict__ dg,
+                                                              int accumulate) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float ss = 0.f, dot = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float x = v[(size_t)r * K + k];
+    ss = fmaf(x, x, ss);
+    dot = fmaf(dw[(size_t)r * K + k], x, dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float n = sqrtf(ss), gn = g[r] / n, c = dot / ss;
+  for (int k = lane; k < K; k += 32) {
+    const size_t o = (size_t)r * K + k;
+    const float t = gn * (dw[o] - v[o] * c);
+    dv[o] = accumulate ? dv[o] + t : t;
+  }
+  if (lane == 0) dg[r] = accumulate ? dg[r] + dot / n : dot / n;
+}
+
 __global__ void __launch_bounds__(256) gather_index_kernel(const long long* __restrict__ src, const long long* __restrict__ idx,
                                                            int n, long long* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = src[idx[i]];
@@ -136,6 +174,18 @@ extern "C" int exvae_reparam_logq_bwd(const float* mu, const float* logvar, cons
   EXVAE_CHECK_ARG(mu && logvar && eps && z && B > 0 && D > 0 && (dmu || dlogvar));
   const long long n = (long long)B * D;
   reparam_logq_bwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(mu, logvar, eps, z, dz, dlogq, n, D, dmu, dlogvar);
+  EXVAE_RETURN_LAST_ERROR();
+}
+
+extern "C" int exvae_weight_norm_fwd(const float* v, const float* g, int R, int K, float* w, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(v && g && w && R > 0 && K > 0);
+  weight_norm_fwd_kernel<<<ceil_div(R, 8), 256, 0, as_stream(stream)>>>(v, g, R, K, w);
+  EXVAE_RETURN_LAST_ERROR();
+}
+extern "C" int exvae_weight_norm_bwd(const float* v, const float* g, const float* dw, int R, int K, float* dv, float* dg,
+                                     int accumulate, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(v && g && dw && dv && dg && R > 0 && K > 0);
+  weight_norm_bwd_kernel<<<ceil_div(R, 8), 256, 0, as_stream(stream)>>>(v, g, dw, R, K, dv, dg, accumulate);
   EXVAE_RETURN_LAST_ERROR();
 }
 

@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv_internal.cuh"
 #include "gemm_tc.cuh"
 
 namespace exvae {
@@ -351,9 +352,10 @@ __global__ void __launch_bounds__(256) dpre_colsum_kernel(const float* __restric
                                                           const float* __restrict__ sig_or_out, int R, int O,
                                                           int act, float lo, float hi, int RL, int iters,
                                                           float* __restrict__ dsplit,
-                                                          float* __restrict__ cs_part) {
+                                                          float* __restrict__ cs_part, int ldd) {
   extern __shared__ float sh_cs[];               // [RL][ncat]
   const int ncat = MODE == 0 ? 2 * O : O;
+  if (ldd == 0) ldd = ncat;                      // row pitch of dsplit (conv layers with ncat % 4 != 0 pad it to 4)
   const int Ov = O / VW;
   const int rbase = blockIdx.x * RL * iters;
   const int cv = threadIdx.x % Ov, lanei = threadIdx.x / Ov;
@@ -379,8 +381,8 @@ __global__ void __launch_bounds__(256) dpre_colsum_kernel(const float* __restric
           a0[k] += dh[k];
           a1[k] += dg[k];
         }
-        vstore<VW>(dsplit + (size_t)r * ncat + VW * cv, dh);
-        vstore<VW>(dsplit + (size_t)r * ncat + O + VW * cv, dg);
+        vstore<VW>(dsplit + (size_t)r * ldd + VW * cv, dh);
+        vstore<VW>(dsplit + (size_t)r * ldd + O + VW * cv, dg);
       } else {
         if (act != EXVAE_ACT_NONE) {
           float o[VW];
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(256) dpre_colsum_kernel(const float* __restric
             else if (act == EXVAE_ACT_RELU) d[k] = o[k] > 0.f ? d[k] : 0.f;
           }
         }
-        vstore<VW>(dsplit + (size_t)r * ncat + VW * cv, d);
+        vstore<VW>(dsplit + (size_t)r * ldd + VW * cv, d);
 #pragma unroll
         for (int k = 0; k < VW; ++k) a0[k] += d[k];
       }
@@ -723,7 +725,7 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
     auto stage_kern = (O % 4 == 0) ? dpre_colsum_kernel<0, 4> : dpre_colsum_kernel<0, 1>;
     stage_kern<<<plan.S2, 256, sh, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, plan.RL, plan.iters,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
-                                                         reinterpret_cast<float*>(w + plan.off_cs));
+                                                         reinterpret_cast<float*>(w + plan.off_cs), 0);
     EXVAE_CUDA(cudaGetLastError());
     const FwdWs f = fwd_ws_layout(R, K, 2 * O, true);
     const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes && al16(fwd_ws);
@@ -783,7 +785,7 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
     auto stage_kern = (O % 4 == 0) ? dpre_colsum_kernel<1, 4> : dpre_colsum_kernel<1, 1>;
     stage_kern<<<plan.S2, 256, sh, st>>>(dout, nullptr, out, R, O, act, lo, hi, plan.RL, plan.iters,
                                                          reinterpret_cast<float*>(w + plan.off_dsplit),
-                                                         reinterpret_cast<float*>(w + plan.off_cs));
+                                                         reinterpret_cast<float*>(w + plan.off_cs), 0);
     EXVAE_CUDA(cudaGetLastError());
     (void)fwd_ws; (void)fwd_ws_bytes;
     return dense_bwd_tc(x, W, nullptr, R, K, O, O, dx, dW, nullptr, db, nullptr, nullptr, plan, w, accumulate, st);
@@ -803,5 +805,196 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
 extern "C" int exvae_gemm_backend(void) { return tc_enabled() ? 1 : 0; }
 extern "C" int exvae_gemm_set_trace(uint64_t* buf) {
   tc_set_trace(reinterpret_cast<unsigned long long*>(buf));
+  return EXVAE_OK;
+}
+
+
+// =====================================================================================================================
+// K4 — convolution entry points (GatedConv2d / Conv2d, utils/nn.py:72-114; weight-normed convs of models/fully_conv.py)
+// =====================================================================================================================
+namespace exvae {
+namespace {
+
+struct ConvPlan {
+  int OH, OW, taps;
+  long long R;
+  int implicit, cpad, Kp;          // forward operand: [ncat][Kp], K index = tap*cpad + c
+  int Kpc;                         // materialised patch rows: pitch round4(taps*Cin), channel pitch Cin
+  int dx_implicit, cpad_dx, Kp_dx; // stride-1 input gradient as a convolution of dcat: operand [Cin][taps*cpad_dx]
+  int ldd;                         // row pitch of dcat (ncat rounded up to 4)
+  int bh, bn, bh_dx, bn_dx;
+};
+inline ConvPlan conv_plan(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int ncat) {
+  ConvPlan c{};
+  c.OH = (H + 2 * pad - KH) / stride + 1;
+  c.OW = (W + 2 * pad - KW) / stride + 1;
+  c.taps = KH * KW;
+  c.R = (long long)N * c.OH * c.OW;
+  c.Kpc = ceil_div(c.taps * Cin, 4) * 4;
+  c.ldd = ceil_div(ncat, 4) * 4;
+  const bool tc = tc_enabled();
+  c.implicit = tc && Cin >= 16 && Cin % 4 == 0 && tc_conv_tiling(c.OH, c.OW, &c.bh, &c.bn);
+  c.cpad = c.implicit ? ceil_div(Cin, 32) * 32 : Cin;
+  c.Kp = c.implicit ? c.taps * c.cpad : c.Kpc;
+  c.dx_implicit = tc && stride == 1 && ncat >= 16 && ncat % 4 == 0 && KH - 1 - pad >= 0 && KW - 1 - pad >= 0 &&
+                  tc_conv_tiling(H, W, &c.bh_dx, &c.bn_dx);
+  c.cpad_dx = ceil_div(ncat, 32) * 32;
+  c.Kp_dx = c.taps * c.cpad_dx;
+  return c;
+}
+
+struct ConvBwdWs {
+  size_t off_dcat, off_cs, off_col, off_part, bytes;
+  TcBwdPlan gp;
+};
+inline ConvBwdWs conv_bwd_ws(const ConvPlan& c, int ncat, int O) {
+  ConvBwdWs w;
+  w.gp = tc_bwd_plan((int)c.R, c.Kpc, ncat);
+  tc_stage_geometry(w.gp, (int)c.R, O);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  w.off_dcat = take(sizeof(float) * (size_t)c.R * c.ldd);
+  w.off_cs = take(sizeof(float) * (size_t)stage_blocks_max((int)c.R) * ncat);
+  w.off_col = take(sizeof(float) * (size_t)c.R * c.Kpc);
+  w.off_part = take(sizeof(float) * (size_t)w.gp.S * ncat * c.Kpc);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+}  // namespace exvae
+
+/* plan[0..8] = {OH, OW, implicit, cpad, Kp, Kpc, dx_implicit, cpad_dx, Kp_dx} */
+extern "C" int exvae_conv_plan(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int ncat, int* plan) {
+  EXVAE_CHECK_ARG(plan && N > 0 && H > 0 && W > 0 && Cin > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0 && ncat > 0);
+  const ConvPlan c = conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat);
+  EXVAE_CHECK_ARG(c.OH > 0 && c.OW > 0);
+  plan[0] = c.OH; plan[1] = c.OW; plan[2] = c.implicit; plan[3] = c.cpad; plan[4] = c.Kp; plan[5] = c.Kpc;
+  plan[6] = c.dx_implicit; plan[7] = c.cpad_dx; plan[8] = c.Kp_dx;
+  return EXVAE_OK;
+}
+
+extern "C" size_t exvae_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad,
+                                                   int ncat) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return 0;
+  const ConvPlan c = conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat);
+  return c.implicit ? 256 : align_up(sizeof(float) * (size_t)c.R * c.Kp, 256);
+}
+
+extern "C" int exvae_conv2d_fwd(const float* x, const float* wpk, const float* b0, const float* b1, int N, int H, int W,
+                                int Cin, int KH, int KW, int stride, int pad, int O, int gated, int act, float lo,
+                                float hi, float* out, float* sig, void* ws, size_t ws_bytes, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(x && wpk && out && N > 0 && H > 0 && W > 0 && Cin > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0 && O > 0);
+  if (!tc_enabled()) return EXVAE_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int ncat = gated ? 2 * O : O;
+  const ConvPlan c = conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat);
+  EXVAE_CHECK_ARG(c.OH > 0 && c.OW > 0 && c.R < (1ll << 31));
+  TcGemm g{};
+  TcConv cv{};
+  if (c.implicit) {
+    cv.x = x; cv.N = N; cv.H = H; cv.W = W; cv.C = Cin; cv.KH = KH; cv.KW = KW; cv.stride = stride; cv.pad = pad;
+    cv.OH = c.OH; cv.OW = c.OW; cv.bh = c.bh; cv.bn = c.bn;
+    g.conv = &cv;
+  } else {
+    if (!ws || ws_bytes < sizeof(float) * (size_t)c.R * c.Kp) return EXVAE_ERR_WORKSPACE;
+    float* col = static_cast<float*>(ws);
+    int rc = conv_im2col(x, N, H, W, Cin, KH, KW, stride, pad, c.OH, c.OW, c.Kp, col, st);
+    if (rc) return rc;
+    g.a = col; g.a_rows = (int)c.R; g.a_cols = c.Kp;
+  }
+  g.a_mn = false;
+  g.b = wpk; g.b_rows = ncat; g.b_cols = c.Kp; g.b_mn = false;
+  g.M = (int)c.R; g.N = O; g.K = c.Kp; g.ldc = O; g.out0 = out;
+  if (gated) {
+    g.epi = TC_GATED; g.gated_O = O; g.bias0 = b0; g.bias1 = b1; g.out2 = sig;
+  } else {
+    g.epi = TC_BIAS_ACT; g.bias0 = b0; g.act = act; g.lo = lo; g.hi = hi;
+  }
+  return tc_gemm_launch(g, st);
+}
+
+extern "C" size_t exvae_conv2d_bwd_workspace_bytes(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int O,
+                                                   int gated) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || O <= 0) return 0;
+  const int ncat = gated ? 2 * O : O;
+  return conv_bwd_ws(conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat), ncat, O).bytes;
+}
+
+/* wbw: the backward operand the plan asks for: dx_implicit ? mode-1 packing [Cin][Kp_dx] : mode-0 packing with
+ * cpad = Cin, [ncat][Kpc] (only read when dx != NULL). */
+extern "C" int exvae_conv2d_bwd(const float* x, const float* wbw, const float* out, const float* sig, const float* dout,
+                                int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int O, int gated,
+                                int act, float lo, float hi, float* dx, float* dW0, float* db0, float* dW1, float* db1,
+                                void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(x && dout && dW0 && ws && N > 0 && H > 0 && W > 0 && Cin > 0 && KH > 0 && KW > 0 && O > 0);
+  EXVAE_CHECK_ARG(!gated || (out && sig && dW1));
+  EXVAE_CHECK_ARG(!dx || wbw);
+  if (!tc_enabled()) return EXVAE_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int ncat = gated ? 2 * O : O;
+  const ConvPlan c = conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat);
+  const ConvBwdWs wl = conv_bwd_ws(c, ncat, O);
+  if (ws_bytes < wl.bytes) return EXVAE_ERR_WORKSPACE;
+  char* w = static_cast<char*>(ws);
+  float* dcat = reinterpret_cast<float*>(w + wl.off_dcat);
+  float* cs = reinterpret_cast<float*>(w + wl.off_cs);
+  float* col = reinterpret_cast<float*>(w + wl.off_col);
+  float* part = reinterpret_cast<float*>(w + wl.off_part);
+  const int R = (int)c.R;
+  // 1. pre-activation gradient dcat [R][ldd] (+ per-block column sums for the bias gradients)
+  if (c.ldd != ncat) EXVAE_CUDA(cudaMemsetAsync(dcat, 0, sizeof(float) * (size_t)R * c.ldd, st));
+  {
+    const TcBwdPlan& gp = wl.gp;
+    const size_t sh = sizeof(float) * gp.RL * ncat;
+    if (gated) {
+      auto k = (O % 4 == 0) ? dpre_colsum_kernel<0, 4> : dpre_colsum_kernel<0, 1>;
+      k<<<gp.S2, 256, sh, st>>>(dout, out, sig, R, O, 0, 0.f, 0.f, gp.RL, gp.iters, dcat, cs, c.ldd);
+    } else {
+      auto k = (O % 4 == 0) ? dpre_colsum_kernel<1, 4> : dpre_colsum_kernel<1, 1>;
+      k<<<gp.S2, 256, sh, st>>>(dout, nullptr, out, R, O, act, lo, hi, gp.RL, gp.iters, dcat, cs, c.ldd);
+    }
+    EXVAE_CUDA(cudaGetLastError());
+  }
+  int rc;
+  // 2. weight gradient: patches recomputed (never saved by the forward), dWcat = dcat^T . col, split over the pixels
+  rc = conv_im2col(x, N, H, W, Cin, KH, KW, stride, pad, c.OH, c.OW, c.Kpc, col, st);
+  if (rc) return rc;
+  {
+    TcGemm g{};
+    g.a = dcat; g.a_rows = R; g.a_cols = c.ldd; g.a_mn = true;
+    g.b = col; g.b_rows = R; g.b_cols = c.Kpc; g.b_mn = true;
+    g.M = ncat; g.N = c.Kpc; g.K = R; g.epi = TC_SPLITK; g.out0 = part; g.ldc = c.Kpc;
+    g.splits = wl.gp.S; g.kchunk = wl.gp.kchunk;
+    rc = tc_gemm_launch(g, st);
+    if (rc) return rc;
+    rc = conv_unpack_wgrad(part, wl.gp.S, ncat, c.Kpc, Cin, O, Cin, KH, KW, dW0, dW1, cs, wl.gp.S2, db0, db1, accumulate, st);
+    if (rc) return rc;
+  }
+  // 3. input gradient
+  if (dx) {
+    if (c.dx_implicit) {
+      // stride 1: dx = conv(dcat, flipped filters) with padding K-1-pad, again an implicit GEMM
+      TcConv cv{};
+      cv.x = dcat; cv.N = N; cv.H = c.OH; cv.W = c.OW; cv.C = ncat; cv.KH = KH; cv.KW = KW; cv.stride = 1;
+      cv.pad = KH - 1 - pad; cv.OH = H; cv.OW = W; cv.bh = c.bh_dx; cv.bn = c.bn_dx;
+      TcGemm g{};
+      g.conv = &cv; g.a_mn = false;
+      g.b = wbw; g.b_rows = Cin; g.b_cols = c.Kp_dx; g.b_mn = false;
+      g.M = N * H * W; g.N = Cin; g.K = c.Kp_dx; g.epi = TC_BIAS_ACT; g.act = EXVAE_ACT_NONE; g.out0 = dx; g.ldc = Cin;
+      rc = tc_gemm_launch(g, st);
+      if (rc) return rc;
+    } else {
+      // dcol [R][Kpc] = dcat . Wcat (A K-major, B MN-major), then the adjoint of im2col (gather form, no atomics)
+      TcGemm g{};
+      g.a = dcat; g.a_rows = R; g.a_cols = c.ldd; g.a_mn = false;
+      g.b = wbw; g.b_rows = ncat; g.b_cols = c.Kpc; g.b_mn = true;
+      g.M = R; g.N = c.Kpc; g.K = c.ldd; g.epi = TC_PLAIN; g.out0 = col; g.ldc = c.Kpc;
+      rc = tc_gemm_launch(g, st);
+      if (rc) return rc;
+      rc = conv_col2im(col, N, H, W, Cin, KH, KW, stride, pad, c.OH, c.OW, c.Kpc, dx, st);
+      if (rc) return rc;
+    }
+  }
   return EXVAE_OK;
 }

@@ -61,6 +61,8 @@ struct TcParams {
   int act; float lo, hi;
   int c_vec;
   TcPriorEpi prior;            // TC_LSE / TC_PW epilogues
+  // implicit-GEMM convolution (CONV): tile = bn images x bh output rows x OW pixels
+  int cv_OH, cv_OW, cv_KW, cv_stride, cv_pad, cv_bh, cv_bn, cv_kbpt, cv_tpi, cv_mrows;
   unsigned long long* trace;   // debug: per-CTA {start, end, tiles, SM} (tools/gemm_trace.py), null in production
 };
 unsigned long long* g_trace = nullptr;
@@ -90,8 +92,10 @@ __device__ __forceinline__ float split_lo(float x) {
 // / TMEM column of the gated tile's second half, bbytes = bytes TMA delivers for the B tile, last = narrow tile maps
 struct TileCoord {
   int m0, n0, kbeg, nkb, z, neff, goff, bbytes, last;
+  int mrows;            // rows of the 128-row tile that hold data (implicit conv tiles may be shorter)
+  int cn0, coh0;        // implicit conv: first image / first output row of the tile
 };
-template <int BN, int EPI, bool B_MN_>
+template <int BN, int EPI, bool B_MN_, int CONV = 0>
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
   TileCoord c;
   const int nt = t % p.ntn;
@@ -99,6 +103,18 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
   const int mt = rest % p.ntm;
   c.z = rest / p.ntm;
   c.m0 = mt * TBM;
+  c.mrows = TBM;
+  c.cn0 = c.coh0 = 0;
+  if (CONV) {
+    if (p.cv_bn == 1) {
+      c.cn0 = mt / p.cv_tpi;
+      c.coh0 = (mt - c.cn0 * p.cv_tpi) * p.cv_bh;
+    } else {
+      c.cn0 = mt * p.cv_bn;
+    }
+    c.m0 = (c.cn0 * p.cv_OH + c.coh0) * p.cv_OW;
+    c.mrows = p.cv_mrows;
+  }
   c.n0 = (EPI == TC_GATED) ? nt * (BN / 2) : nt * BN;
   c.last = nt == p.ntn - 1;
   c.neff = c.last ? p.neff_last : BN;
@@ -123,7 +139,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
 // is what bounds this kernel (measured: TMA-only 0.33, + conversion 0.59, + MMAs 0.91 us per k-block, additive;
 // profiles/r1_gemm_persistent.md).  A stage is 48 KB, so the ring has 4 of them.  An MN-major A tile needs no
 // swizzle (no MMA reads it): one {128 m, 32 k} box, column m read by lane m without bank conflicts.
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CONV = 0>
 __global__ void __launch_bounds__(TTHREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
@@ -180,15 +196,21 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     if (elect_one_sync()) {
       int it = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
+        const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
         for (int kb = 0; kb < c.nkb; ++kb, ++it) {
           const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], A_BYTES + c.bbytes);
+          mbar_arrive_expect_tx(&full[s], (CONV ? c.mrows * 128 : A_BYTES) + c.bbytes);
           unsigned char* sa = smem + s * STAGE_BYTES;
           unsigned char* sb = sa + B_OFF;
           const int k0 = c.kbeg + kb * TBK;
-          if (!A_MN) {
+          if (CONV) {
+            // k-block kb = (tap, 32-channel chunk): ONE box {32 c, OW pixels, bh rows, bn images} of the NHWC input,
+            // shifted by the tap; TMA zero-fills the padding border and the channels beyond C
+            const int tap = kb / p.cv_kbpt, cb = kb - tap * p.cv_kbpt;
+            const int kh = tap / p.cv_KW, kw = tap - kh * p.cv_KW;
+            tma_load_4d(sa, &tmA, &full[s], cb * 32, kw - p.cv_pad, c.coh0 * p.cv_stride + kh - p.cv_pad, c.cn0);
+          } else if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[s], k0, c.m0);                        // box {32 k, 128 rows}
           } else {
             tma_load_2d(sa, &tmA, &full[s], c.m0, k0);                        // box {128 m, 32 k}, no swizzle
@@ -216,7 +238,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       constexpr uint32_t idesc_full = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
-        const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
+        const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
         const int acc = j & 1;
         const uint32_t idesc = c.last ? umma_idesc(TBM, c.neff, false, B_MN) : idesc_full;
         mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     const int am = 32 * qd + lane;                         // tile row (= TMEM lane) of this thread
     int it = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
+      const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
       for (int kb = 0; kb < c.nkb; ++kb, ++it) {
         const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
         mbar_wait(&full[s], ph);
@@ -315,6 +337,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     const int q = warp & 3;       // TMEM lane quadrant this warp may access
     float* patch = reinterpret_cast<float*>(smem + TSTAGES * STAGE_BYTES + 256) + (warp - EPI_WARP0) * (32 * EP_LD);
     int j = 0;
+    int tile_m0 = 0, tile_rows = TBM;     // current tile: first row and number of rows that hold data
     // write the staged 32x32 patch to dst[(row0 + r) * ldc + col0 + c] for c < ncols
     auto flush = [&](float* dst, int row0, int col0, int ncols) {
       const int ldc = (EPI == TC_PW) ? p.prior.ldw : p.ldc;
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + (lane >> 3), ch = (lane & 7) * 4;
           const float4 v = *reinterpret_cast<const float4*>(patch + r * EP_LD + ch);
-          if (row0 + r < p.M) {
+          if (row0 + r < p.M && row0 - tile_m0 + r < tile_rows) {
             float* d = dst + (size_t)(row0 + r) * ldc + col0 + ch;
             if (ch + 3 < ncols) {
               *reinterpret_cast<float4*>(d) = v;
@@ -337,15 +360,18 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         }
       } else {
         if (lane < ncols)
-          for (int r = 0; r < 32 && row0 + r < p.M; ++r) dst[(size_t)(row0 + r) * ldc + col0 + lane] = patch[r * EP_LD + lane];
+          for (int r = 0; r < 32 && row0 + r < p.M && row0 - tile_m0 + r < tile_rows; ++r)
+            dst[(size_t)(row0 + r) * ldc + col0 + lane] = patch[r * EP_LD + lane];
       }
       __syncwarp();
     };
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
-      const TileCoord c = tile_coord<BN, EPI, B_MN>(p, t);
+      const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
       const int acc = j & 1;
       mbar_wait(&acc_full[acc], (j >> 1) & 1);
       tc_fence_after();
+      tile_m0 = c.m0;
+      tile_rows = c.mrows;
       const int row0 = c.m0 + 32 * q;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * ACC_COLS);
       float* prow = patch + lane * EP_LD;
@@ -524,12 +550,12 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
     reinterpret_cast<float4*>(out)[i] = i < n4 ? reinterpret_cast<const float4*>(w0)[i] : reinterpret_cast<const float4*>(w1)[i - n4];
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CONV = 0>
 int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, TcParams& p,
            cudaStream_t st) {
   constexpr int STAGE = TBM * TBK * 4 + 2 * BN * TBK * 4;
   constexpr int SMEM = TSTAGES * STAGE + 1024 + 256 + EP_BYTES;
-  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI, CONV>;
   static bool configured = false;
   if (!configured) {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -537,6 +563,7 @@ int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const 
   }
   p.ntn = EPI == TC_GATED ? ceil_div(g.gated_O, BN / 2) : ceil_div(g.N, BN);
   p.ntm = ceil_div(g.M, TBM);
+  if (CONV) p.ntm = g.conv->bn == 1 ? g.conv->N * (g.conv->OH / g.conv->bh) : ceil_div(g.conv->N, g.conv->bn);
   p.ntiles = p.ntn * p.ntm * (EPI == TC_SPLITK ? g.splits : 1);
   const int grid = std::min(p.ntiles, sm_count());     // persistent: one CTA per SM
   kern<<<grid, TTHREADS, SMEM, st>>>(ma, mb, mbl, p);
@@ -586,8 +613,14 @@ template <int BN>
 static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   CUtensorMap ma, mb, mbl;
   // A never feeds an MMA from shared memory: an MN-major tile is one un-swizzled {128 m, 32 k} box
-  int rc = g.a_mn ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
-                  : make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, false);
+  int rc;
+  if (g.conv) {
+    const TcConv& cv = *g.conv;
+    rc = make_map_nhwc(&ma, cv.x, cv.N, cv.H, cv.W, cv.C, cv.OW, cv.bh, cv.bn, cv.stride);
+  } else {
+    rc = g.a_mn ? make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
+                : make_map2d(&ma, g.a, g.a_rows, g.a_cols, TBM, false);
+  }
   if (rc) return rc;
   rc = make_map2d(&mb, g.b, g.b_rows, g.b_cols, g.b_mn ? 32 : (g.epi == TC_GATED ? BN / 2 : BN), g.b_mn);
   if (rc) return rc;
@@ -611,6 +644,12 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   p.bias0 = g.bias0; p.bias1 = g.bias1; p.out0 = g.out0; p.out1 = g.out1; p.out2 = g.out2; p.ldc = g.ldc;
   p.act = g.act; p.lo = g.lo; p.hi = g.hi;
   p.prior = g.prior;
+  if (g.conv) {
+    const TcConv& cv = *g.conv;
+    p.cv_OH = cv.OH; p.cv_OW = cv.OW; p.cv_KW = cv.KW; p.cv_stride = cv.stride; p.cv_pad = cv.pad;
+    p.cv_bh = cv.bh; p.cv_bn = cv.bn; p.cv_kbpt = ceil_div(cv.C, 32); p.cv_tpi = cv.OH / cv.bh;
+    p.cv_mrows = cv.bn * cv.bh * cv.OW;
+  }
   p.trace = g_trace;
   if (g_trace) g_trace += 8 * 160;   // the next traced launch writes the next segment
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -620,6 +659,12 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   if constexpr (BN == 64) {      // the dual-accumulator prior epilogues only exist for 64-wide tiles (TMEM budget)
     if (g.epi == TC_LSE && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_LSE>(g, ma, mb, mbl, p, st);
     if (g.epi == TC_PW && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_PW>(g, ma, mb, mbl, p, st);
+  }
+  if (g.conv) {      // implicit-GEMM convolution: forward (gated / bias+activation) and the stride-1 input gradient (plain)
+    if (g.a_mn || g.b_mn) return EXVAE_ERR_UNSUPPORTED;
+    if (g.epi == TC_GATED) return launch<BN, false, false, TC_GATED, 1>(g, ma, mb, mbl, p, st);
+    if (g.epi == TC_BIAS_ACT) return launch<BN, false, false, TC_BIAS_ACT, 1>(g, ma, mb, mbl, p, st);
+    return EXVAE_ERR_UNSUPPORTED;
   }
   if (g.epi == TC_GATED && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_GATED>(g, ma, mb, mbl, p, st);
   if (g.epi == TC_BIAS_ACT && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_BIAS_ACT>(g, ma, mb, mbl, p, st);
@@ -634,6 +679,17 @@ static bool tc_use_bn64(const TcGemm& g) {
   const int ntn = g.epi == TC_GATED ? ceil_div(g.gated_O, 64) : ceil_div(g.N, 128);
   return 2 * ceil_div(g.M, TBM) * ntn <= sm_count();
 }
+bool tc_conv_tiling(int OH, int OW, int* bh, int* bn) {
+  if (OW > TBM || OW < 1 || OH < 1) return false;
+  int best = 1;
+  for (int d = 1; d <= OH; ++d)
+    if (OH % d == 0 && d * OW <= TBM) best = d;
+  *bh = best;
+  *bn = best == OH ? std::max(1, TBM / (OH * OW)) : 1;
+  if (*bn > 256) *bn = 256;
+  return true;
+}
+
 int tc_gemm_ntn(const TcGemm& g) { return ceil_div(g.N, tc_use_bn64(g) ? 64 : 128); }
 
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {

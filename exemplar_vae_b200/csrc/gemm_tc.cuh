@@ -21,6 +21,21 @@ struct TcPriorEpi {
   float* wt; int ldwt;     // TC_PW
 };
 
+// Implicit-GEMM convolution: the A operand is never materialised.  Row m of A is output pixel m (NHWC, pixel index
+// = (n*OH + oh)*OW + ow) and its K axis is (tap, channel) with channels padded to a multiple of 32 per tap:
+//   A[m, (kh*KW + kw)*cpad + c] = x[n, oh*stride + kh - pad, ow*stride + kw - pad, c]      (0 outside the image)
+// A 128-row tile is bn images x bh output rows x all OW pixels of each row, so that every k-block (one tap, 32
+// channels) is ONE 4-D TMA box of the activation tensor; B holds the packed weights [N][taps*cpad] (K-major).
+struct TcConv {
+  const float* x;          // [N][H][W][C] fp32, 16-byte aligned, (C*4) % 16 == 0
+  int N, H, W, C;
+  int KH, KW, stride, pad;
+  int OH, OW;
+  int bh, bn;              // tile = bn images x bh rows x OW pixels <= 128 rows; bh | OH; bn > 1 only if bh == OH
+};
+// tile geometry for an output of OH x OW pixels; false if the shape cannot be tiled (OW > 128)
+bool tc_conv_tiling(int OH, int OW, int* bh, int* bn);
+
 // D[M,N] = A[M,K] * B[N,K]^T (+ epilogue).  Operands are plain fp32 row-major matrices [rows][cols] (16-byte aligned
 // base and row pitch); the kernel splits them into tf32 hi/lo parts in shared memory.
 //   a_mn == false: A is [M rows][K cols] (K contiguous)       "K-major"
@@ -36,6 +51,7 @@ struct TcGemm {
   int act; float lo, hi;
   int splits, kchunk;  // TC_SPLITK: grid.z = splits, out0 = partial [splits][M][N]
   TcPriorEpi prior;    // TC_LSE / TC_PW
+  const TcConv* conv;  // non-null: A is the implicit patch matrix of this convolution (a, a_rows, a_cols unused; a_mn = false)
 };
 
 bool tc_enabled();                       // sm_100 device, driver entry point found, not disabled by EXVAE_GEMM=simt

@@ -1,4 +1,5 @@
-// K2 — fused kNN exemplar selection (sm_100a): distance tiles + per-row running top-k in ONE kernel.
+// K2 — fused kNN exemplar selection (sm_100a): distance tiles + per-row running top-k in one kernel, then a
+// one-warp-per-row merge of the per-split lists.
 //
 //   pairwise_distance(z, sub_cache).topk(k, largest=False)      models/BaseModel.py:263-264   (metric 0)
 //   ((z[:,None]-mu[None])**2).sum(2)**0.5 .topk(k=20)           utils/knn_on_latent.py:4-9    (metric 1)
@@ -9,8 +10,9 @@
 // of exact fp32 products, combined in the reference's operation order, ONE rounding to fp32 (metric 0), or the
 // reference's fp32 direct-difference sum + sqrt (metric 1).  Values that beat the row's current k-th best go to a
 // per-row candidate list in shared memory and a warp per row inserts them into the sorted (distance, position) list
-// (ties -> lowest position).  The per-split lists are merged by the LAST CTA of each row block (atomic ticket), so
-// the selection is one launch, deterministic, and graph-capturable.
+// (ties -> lowest position).  knn_fused_merge_kernel then merges the [nsplit, B, k] lists with one warp per row
+// spread over many CTAs (merging inside the tile kernel by the last CTA of a row block was measured 10x slower: 64
+// rows x nsplit lists on ONE SM).  No host sync, deterministic, graph-capturable.
 #include "common.cuh"
 
 namespace exvae {
@@ -52,15 +54,12 @@ struct KfSmem {
   int cand_n[KF_T];
   float thr_v[KF_T];      // current k-th best per row (+inf until the list is full)
   int thr_i[KF_T];
-  int is_last;
 };
 
 template <int METRIC>
 __global__ void __launch_bounds__(256) knn_fused_kernel(const float* __restrict__ z, const float* __restrict__ bank, int B,
                                                         int C, int D, int k, long long pos_offset, int nsplit,
-                                                        float* __restrict__ part_v, int* __restrict__ part_i,
-                                                        unsigned int* __restrict__ tickets,
-                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+                                                        float* __restrict__ part_v, int64_t* __restrict__ part_i) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KfSmem& S = *reinterpret_cast<KfSmem*>(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
@@ -181,67 +180,77 @@ __global__ void __launch_bounds__(256) knn_fused_kernel(const float* __restrict_
     __syncthreads();
   }
 
-  // ---- emit this split's lists, then the last CTA of the row block merges all splits
+  // ---- emit this split's sorted list (global positions; -1 = fewer than k candidates in this split)
   for (int e = tid; e < KF_T * k; e += 256) {
     const int r = e / k, j = e - r * k;
     if (m0 + r < B) {
       const size_t o = ((size_t)split * B + (m0 + r)) * k + j;
+      const int i = S.best_i[r][j];
       part_v[o] = S.best_v[r][j];
-      part_i[o] = S.best_i[r][j];
+      part_i[o] = i == 0x7fffffff ? (int64_t)-1 : (int64_t)i + pos_offset;
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int prev = atomicAdd(&tickets[rb], 1u);
-    S.is_last = prev == (unsigned int)(nsplit - 1);
-    if (S.is_last) tickets[rb] = 0u;     // self-resetting: the next launch finds zeros again
-  }
-  __syncthreads();
-  if (!S.is_last) return;
-  __threadfence();
-  for (int r = warp; r < KF_T; r += 8) {
-    const int b = m0 + r;
-    if (b >= B) continue;     // warp-uniform
-    float lv = INFINITY;
-    int li = 0x7fffffff;
-    for (int s = 0; s < nsplit; ++s) {
-      const size_t o = ((size_t)s * B + b) * k;
-      // a split's list is sorted: stop at its first entry that does not enter the merged list
-      for (int j = 0; j < k; ++j) {
-        const float v = __ldcg(part_v + o + j);
-        const int i = __ldcg(part_i + o + j);
-        if (i == 0x7fffffff) break;
-        const float kv = __shfl_sync(0xffffffffu, lv, k - 1);
-        const int ki = __shfl_sync(0xffffffffu, li, k - 1);
-        if (!kf_less(v, i, kv, ki)) break;
-        kf_insert(lv, li, v, i, lane, k);
+}
+
+// Merge the per-split lists: one warp per row over nsplit*k candidates keyed by (dist, global position); pass p picks
+// the smallest key strictly greater than pick p-1 (all loads of a pass are independent).
+__global__ void __launch_bounds__(256) knn_fused_merge_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dist,
+                                                              int G, int B, int k, int64_t* __restrict__ out_idx,
+                                                              float* __restrict__ out_dist) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int n = G * k;
+  float lv = -INFINITY;
+  long long li = -1;
+  for (int p = 0; p < k; ++p) {
+    float bv = INFINITY;
+    long long bi = INT64_MAX;
+    for (int c = lane; c < n; c += 32) {
+      const int g = c / k, j = c - g * k;
+      const size_t o = ((size_t)g * B + b) * k + j;
+      const float v = dist[o];
+      const long long i = idx[o];
+      if (i < 0) continue;
+      const bool after = (v > lv) || (v == lv && i > li);
+      if (after && (v < bv || (v == bv && i < bi))) {
+        bv = v;
+        bi = i;
       }
     }
-    if (lane < k) {
-      const bool found = li != 0x7fffffff;
-      out_idx[(size_t)b * k + lane] = found ? (int64_t)li + pos_offset : (int64_t)-1;
-      out_dist[(size_t)b * k + lane] = found ? lv : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
     }
+    if (lane == 0) {
+      out_idx[(size_t)b * k + p] = bi == INT64_MAX ? -1 : bi;
+      out_dist[(size_t)b * k + p] = bv;
+    }
+    lv = bv;
+    li = bi;
   }
 }
 
 inline int knn_splits(int B, int C) {
   const int rb = ceil_div(B, KF_T);
   const int ntile = ceil_div(C, KF_T);
-  return std::max(1, std::min(ntile, ceil_div(2 * sm_count(), rb)));
+  return std::max(1, std::min(ntile, ceil_div(sm_count(), rb)));
 }
 
 struct KnnWs {
-  size_t off_v, off_i, off_t, bytes;
+  size_t off_v, off_i, bytes;
 };
 inline KnnWs knn_ws(int B, int C, int k) {
   KnnWs w;
   const int ns = knn_splits(B, C);
   size_t off = 0;
-  w.off_t = off; off += align_up(sizeof(unsigned int) * (size_t)ceil_div(B, KF_T), 256);
   w.off_v = off; off += align_up(sizeof(float) * (size_t)ns * B * k, 256);
-  w.off_i = off; off += align_up(sizeof(int) * (size_t)ns * B * k, 256);
+  w.off_i = off; off += align_up(sizeof(int64_t) * (size_t)ns * B * k, 256);
   w.bytes = off;
   return w;
 }
@@ -267,18 +276,18 @@ extern "C" int exvae_knn_topk(const float* z, const float* bank, int B, int C, i
   if (ws_bytes < w.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   char* base = static_cast<char*>(ws);
-  unsigned int* tickets = reinterpret_cast<unsigned int*>(base + w.off_t);
-  // the workspace is caller-owned and may be uninitialised: zero the tickets (a memset node, no kernel)
-  EXVAE_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned int) * (size_t)ceil_div(B, KF_T), st));
+  float* pv = reinterpret_cast<float*>(base + w.off_v);
+  int64_t* pi = reinterpret_cast<int64_t*>(base + w.off_i);
   const int ns = knn_splits(B, C);
   dim3 grid(ns, ceil_div(B, KF_T));
   auto launch = [&](auto kern) -> int {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KfSmem)));
-    kern<<<grid, 256, sizeof(KfSmem), st>>>(z, bank, B, C, D, k, (long long)pos_offset, ns,
-                                            reinterpret_cast<float*>(base + w.off_v),
-                                            reinterpret_cast<int*>(base + w.off_i), tickets, out_idx, out_dist);
+    kern<<<grid, 256, sizeof(KfSmem), st>>>(z, bank, B, C, D, k, (long long)pos_offset, ns, pv, pi);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? EXVAE_OK : (int)e;
   };
-  return metric == 0 ? launch(knn_fused_kernel<0>) : launch(knn_fused_kernel<1>);
+  int rc = metric == 0 ? launch(knn_fused_kernel<0>) : launch(knn_fused_kernel<1>);
+  if (rc) return rc;
+  knn_fused_merge_kernel<<<ceil_div(B, 8), 256, 0, st>>>(pi, pv, ns, B, k, out_idx, out_dist);
+  EXVAE_RETURN_LAST_ERROR();
 }

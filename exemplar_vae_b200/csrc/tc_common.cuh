@@ -20,6 +20,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
 // generic-proxy shared-memory writes -> visible to async-proxy readers (tcgen05.mma operand fetch, TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -188,6 +196,23 @@ inline int make_map2d(CUtensorMap* map, const float* base, int rows, int cols, i
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EXVAE_OK : EXVAE_ERR_UNSUPPORTED;
+}
+// 4-D map over an NHWC fp32 activation tensor [N][H][W][C] for the implicit-GEMM convolution: box = {32 channels,
+// bw pixels, bh rows, bn images} taken every `stride`-th pixel / row (element strides; TMA then wants box extents of
+// count * stride), SWIZZLE_128B: the box lands as [bn*bh*bw rows][32 floats], i.e. a K-major operand tile whose rows
+// are output pixels.  Out-of-image coordinates (the convolution's zero padding, channels beyond C) are zero-filled.
+inline int make_map_nhwc(CUtensorMap* map, const float* base, int N, int H, int W, int C, int bw, int bh, int bn,
+                         int stride) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return EXVAE_ERR_UNSUPPORTED;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EXVAE_OK : EXVAE_ERR_UNSUPPORTED;
 }

@@ -154,8 +154,7 @@ class WNConv2d(nn.Module):
         self._stride, self._pad = _pair(stride)[0], _pair(padding)[0]
 
     def weight(self):
-        v = self.weight_v
-        return v * (self.weight_g / v.flatten(1).norm(dim=1).view(-1, 1, 1, 1))
+        return ops.weight_norm(self.weight_v, self.weight_g)
 
     def forward(self, x, act=ACT_NONE, lo=0.0, hi=0.0):
         return ops.conv2d(x, self.weight(), self.bias, self._stride, self._pad, act, lo, hi)

@@ -1058,66 +1058,148 @@ def prior_lse_sharded(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total: int, gr
 
 
 # ======================================================================================
-# K4: convolution = im2col -> dense GEMM (fused epilogue) -> col2im ; ELU ; 2x upsample   (NHWC)
+# K4: convolution (NHWC): implicit GEMM on tcgen05 (>= 16 input channels), patch-matrix GEMM otherwise; ELU; 2x upsample
 # ======================================================================================
 def _conv_out(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
-class _Im2Col(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, kh, kw, stride, pad):
-        L = lib()
-        x = _f32(x, "x")
-        N, H, W, C = x.shape
-        OH, OW = _conv_out(H, kh, stride, pad), _conv_out(W, kw, stride, pad)
-        col = torch.empty((N * OH * OW, kh * kw * C), dtype=torch.float32, device=x.device)
-        L.check(L.exvae_im2col_nhwc(_p(x), N, H, W, C, kh, kw, stride, pad, _p(col), _stream()), "im2col")
+def _conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat):
+    import ctypes
+    L = lib()
+    arr = (ctypes.c_int * 9)()
+    L.check(L.exvae_conv_plan(N, H, W, Cin, KH, KW, stride, pad, ncat, ctypes.addressof(arr)), "conv_plan")
+    keys = ("OH", "OW", "implicit", "cpad", "Kp", "Kpc", "dx_implicit", "cpad_dx", "Kp_dx")
+    return dict(zip(keys, list(arr)))
+
+
+def _pack_filters(W0, W1, mode, cpad, Kp, rows_total):
+    """[rows_total][Kp] operand from the reference-layout filters ([Cout,Cin,KH,KW]); gated layers: h then g."""
+    L = lib()
+    O, Cin, KH, KW = W0.shape
+    out = torch.empty((rows_total, Kp), dtype=torch.float32, device=W0.device)
+    L.check(L.exvae_conv_pack_weight(_p(W0), O, Cin, KH, KW, mode, cpad, Kp, 0, 1, rows_total, _p(out), _stream()),
+            "conv_pack_weight")
+    _count(1)
+    if W1 is not None:
+        L.check(L.exvae_conv_pack_weight(_p(W1), O, Cin, KH, KW, mode, cpad, Kp, O, 0, rows_total, _p(out), _stream()),
+                "conv_pack_weight")
         _count(1)
-        ctx.cfg = (N, H, W, C, kh, kw, stride, pad)
-        return col
+    return out
+
+
+class _Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W0, b0, W1, b1, stride, pad, act, lo, hi, sink):
+        L = lib()
+        x, W0 = _f32(x, "x"), _f32(W0, "weight")
+        gated = W1 is not None
+        W1 = _f32(W1) if gated else None
+        b0 = _f32(b0) if b0 is not None else None
+        b1 = _f32(b1) if b1 is not None else None
+        N, H, Wd, C = x.shape
+        O, Cin, KH, KW = W0.shape
+        assert Cin == C
+        ncat = 2 * O if gated else O
+        pl = _conv_plan(N, H, Wd, C, KH, KW, stride, pad, ncat)
+        wpk = _pack_filters(W0, W1, 0, pl["cpad"], pl["Kp"], ncat)
+        out = torch.empty((N, pl["OH"], pl["OW"], O), dtype=torch.float32, device=x.device)
+        need = any(ctx.needs_input_grad)
+        sig = torch.empty_like(out) if (gated and need) else None
+        ws = _ws(L.exvae_conv2d_fwd_workspace_bytes(N, H, Wd, C, KH, KW, stride, pad, ncat), x.device)
+        L.check(L.exvae_conv2d_fwd(_p(x), _p(wpk), _p(b0), _p(b1), N, H, Wd, C, KH, KW, stride, pad, O, 1 if gated else 0,
+                                   act, lo, hi, _p(out), _p(sig), _p(ws), ws.numel(), _stream()), "conv2d_fwd")
+        _count(1 if pl["implicit"] else 2)
+        keep_out = need and (gated or act != ACT_NONE)
+        ctx.save_for_backward(x, W0, W1, out if keep_out else None, sig)
+        ctx.cfg = (stride, pad, act, lo, hi, b0 is not None, b1 is not None)
+        ctx.sink = sink
+        return out
 
     @staticmethod
-    def backward(ctx, dcol):
+    def backward(ctx, dout):
         L = lib()
-        N, H, W, C, kh, kw, stride, pad = ctx.cfg
-        dcol = _f32(dcol)
-        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dcol.device)
-        L.check(L.exvae_col2im_nhwc(_p(dcol), N, H, W, C, kh, kw, stride, pad, _p(dx), _stream()), "col2im")
-        _count(1)
-        return dx, None, None, None, None
-
-
-def _patches(x, kh, kw, stride, pad):
-    N, H, W, C = x.shape
-    if kh == 1 and kw == 1 and stride == 1 and pad == 0:
-        return x.reshape(N * H * W, C)
-    return _Im2Col.apply(x, kh, kw, stride, pad)
-
-
-def _w2d(w):
-    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] (channel fastest, matching the NHWC patch matrix)."""
-    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+        x, W0, W1, out, sig = ctx.saved_tensors
+        stride, pad, act, lo, hi, has_b0, has_b1 = ctx.cfg
+        gated = W1 is not None
+        dout = _f32(dout)
+        N, H, Wd, C = x.shape
+        O, Cin, KH, KW = W0.shape
+        ncat = 2 * O if gated else O
+        pl = _conv_plan(N, H, Wd, C, KH, KW, stride, pad, ncat)
+        dx, wbw = None, None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if pl["dx_implicit"]:
+                wbw = _pack_filters(W0, W1, 1, pl["cpad_dx"], pl["Kp_dx"], Cin)
+            else:
+                wbw = _pack_filters(W0, W1, 0, Cin, pl["Kpc"], ncat)
+        sink = ctx.sink
+        if sink is not None:
+            dW0, db0, dW1, db1 = sink
+        else:
+            dW0 = torch.empty_like(W0)
+            dW1 = torch.empty_like(W1) if gated else None
+            db0 = torch.empty((O,), dtype=torch.float32, device=x.device) if has_b0 else None
+            db1 = torch.empty((O,), dtype=torch.float32, device=x.device) if has_b1 else None
+        ws = _ws(L.exvae_conv2d_bwd_workspace_bytes(N, H, Wd, C, KH, KW, stride, pad, O, 1 if gated else 0), x.device)
+        L.check(L.exvae_conv2d_bwd(_p(x), _p(wbw), _p(out), _p(sig), _p(dout), N, H, Wd, C, KH, KW, stride, pad, O,
+                                   1 if gated else 0, act, lo, hi, _p(dx), _p(dW0), _p(db0), _p(dW1), _p(db1), _p(ws),
+                                   ws.numel(), 1 if sink is not None else 0, _stream()), "conv2d_bwd")
+        _count(4 + (0 if dx is None else (1 if pl["dx_implicit"] else 2)))
+        if sink is not None:
+            _sink_done(sink)
+            return dx, None, None, None, None, None, None, None, None, None, None
+        return dx, dW0, db0, dW1, db1, None, None, None, None, None, None
 
 
 def conv2d_gated(x, Wh, bh, Wg, bg, stride: int, pad: int) -> torch.Tensor:
     """GatedConv2d (utils/nn.py:72-95, activation=None): conv_h(x) * sigmoid(conv_g(x)); x, result NHWC."""
-    N, H, W, C = x.shape
-    Cout, Cin, kh, kw = Wh.shape
-    assert Cin == C
-    col = _patches(x, kh, kw, stride, pad)
-    out = gated_dense(col, _w2d(Wh), bh, _w2d(Wg), bg)
-    return out.view(N, _conv_out(H, kh, stride, pad), _conv_out(W, kw, stride, pad), Cout)
+    return _Conv2dFn.apply(x, Wh, bh, Wg, bg, int(stride), int(pad), ACT_NONE, 0.0, 0.0, _grad_sink(Wh, bh, Wg, bg))
 
 
 def conv2d(x, W, b=None, stride: int = 1, pad: int = 0, act: int = ACT_NONE, lo: float = 0.0, hi: float = 0.0):
     """nn.Conv2d + fused activation; x, result NHWC."""
-    N, H, Wd, C = x.shape
-    Cout, Cin, kh, kw = W.shape
-    assert Cin == C
-    col = _patches(x, kh, kw, stride, pad)
-    out = linear(col, _w2d(W), b, act, lo, hi)
-    return out.view(N, _conv_out(H, kh, stride, pad), _conv_out(Wd, kw, stride, pad), Cout)
+    sk = _grad_sink(W, b)
+    return _Conv2dFn.apply(x, W, b, None, None, int(stride), int(pad), int(act), float(lo), float(hi),
+                           None if sk is None else (sk[0], sk[1], None, None))
+
+
+class _WeightNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, g, sink):
+        L = lib()
+        v, g = _f32(v), _f32(g)
+        R = v.shape[0]
+        K = v.numel() // R
+        w = torch.empty_like(v)
+        L.check(L.exvae_weight_norm_fwd(_p(v), _p(g), R, K, _p(w), _stream()), "weight_norm")
+        _count(1)
+        ctx.save_for_backward(v, g)
+        ctx.sink = sink
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        L = lib()
+        v, g = ctx.saved_tensors
+        dw = _f32(dw)
+        R = v.shape[0]
+        K = v.numel() // R
+        sink = ctx.sink
+        dv, dg = sink if sink is not None else (torch.empty_like(v), torch.empty_like(g))
+        L.check(L.exvae_weight_norm_bwd(_p(v), _p(g), _p(dw), R, K, _p(dv), _p(dg), 1 if sink is not None else 0, _stream()),
+                "weight_norm_bwd")
+        _count(1)
+        if sink is not None:
+            _sink_done(sink)
+            return None, None, None
+        return dv, dg, None
+
+
+def weight_norm(v, g) -> torch.Tensor:
+    """torch.nn.utils.weight_norm: w = g * v / ||v|| with the norm over everything but dim 0 (models/fully_conv.py:17)."""
+    return _WeightNorm.apply(v, g, _grad_sink(v, g))
 
 
 class _Elu(torch.autograd.Function):

@@ -194,6 +194,40 @@ EXVAE_API int exvae_col2im_nhwc(const float* dcol, int N, int H, int W, int C, i
 /* torch.nn.ELU (alpha = 1); the backward takes the forward OUTPUT y */
 EXVAE_API int exvae_elu_fwd(const float* x, int64_t n, float* y, exvae_stream_t stream);
 EXVAE_API int exvae_elu_bwd(const float* y, const float* dy, int64_t n, float* dx, exvae_stream_t stream);
+/* ---------------------------------------------------------------- convolution (K4)
+ * GatedConv2d / Conv2d (utils/nn.py:72-114) and the weight-normed convolutions of models/fully_conv.py, NHWC.
+ * Layers with >= 16 input channels run as an IMPLICIT GEMM on tcgen05 (no patch matrix in HBM: one 4-D TMA box of the
+ * activation tensor per filter tap and 32-channel chunk, zero padding by TMA's out-of-bounds fill); so does the input
+ * gradient of stride-1 layers (convolution of the pre-activation gradient with the flipped filters).  Layers with
+ * fewer input channels, the weight gradient and the input gradient of stride-2 layers use a patch matrix whose rows
+ * are padded to 4 floats (every GEMM on tcgen05).
+ * exvae_conv_plan: plan[0..8] = {OH, OW, implicit, cpad, Kp, Kpc, dx_implicit, cpad_dx, Kp_dx}; ncat = 2*O (gated) or O.
+ *   forward operand  wpk [ncat][Kp]   = exvae_conv_pack_weight(mode 0, cpad, Kp)  (gated: h rows then g rows)
+ *   backward operand wbw              = dx_implicit ? mode 1, cpad_dx, Kp_dx, rows = Cin : mode 0, cpad = Cin, Kpc
+ * pack_weight: w [Cout][Cin][KH][KW] (the reference's nn.Conv2d layout) -> rows [row_off, row_off+Cout) (mode 0) or
+ * columns row_off.. of every tap (mode 1) of `out` [rows_total][Kp]; zero_first clears `out` (padding must be 0). */
+EXVAE_API int exvae_conv_plan(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int ncat, int* plan);
+EXVAE_API int exvae_conv_pack_weight(const float* w, int Cout, int Cin, int KH, int KW, int mode, int cpad, int Kp,
+                                     int row_off, int zero_first, int rows_total, float* out, exvae_stream_t stream);
+EXVAE_API size_t exvae_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad,
+                                                  int ncat);
+/* out [N,OH,OW,O] = act(conv(x, W0) + b0)                      (gated = 0; act as in exvae_linear_fwd)
+ *                 = (conv(x,W0)+b0) * sigmoid(conv(x,W1)+b1)   (gated = 1; sig [N,OH,OW,O] saved for the backward) */
+EXVAE_API int exvae_conv2d_fwd(const float* x, const float* wpk, const float* b0, const float* b1, int N, int H, int W,
+                               int Cin, int KH, int KW, int stride, int pad, int O, int gated, int act, float lo,
+                               float hi, float* out, float* sig, void* ws, size_t ws_bytes, exvae_stream_t stream);
+EXVAE_API size_t exvae_conv2d_bwd_workspace_bytes(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int O,
+                                                  int gated);
+/* dx [N,H,W,Cin] (nullable), dW0/dW1 [O][Cin][KH][KW], db0/db1 [O] (nullable); accumulate != 0 adds into them. */
+EXVAE_API int exvae_conv2d_bwd(const float* x, const float* wbw, const float* out, const float* sig, const float* dout,
+                               int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int O, int gated,
+                               int act, float lo, float hi, float* dx, float* dW0, float* db0, float* dW1, float* db1,
+                               void* ws, size_t ws_bytes, int accumulate, exvae_stream_t stream);
+/* torch.nn.utils.weight_norm (models/fully_conv.py:17): w[r,:] = g[r] * v[r,:] / ||v[r,:]||_2 for R rows of length K;
+ * backward: dv, dg from dw (accumulate != 0 adds into them). */
+EXVAE_API int exvae_weight_norm_fwd(const float* v, const float* g, int R, int K, float* w, exvae_stream_t stream);
+EXVAE_API int exvae_weight_norm_bwd(const float* v, const float* g, const float* dw, int R, int K, float* dv, float* dg,
+                                    int accumulate, exvae_stream_t stream);
 /* nn.Upsample(scale_factor=2) (nearest), NHWC: y [N,2H,2W,C]; backward sums each 2x2 block */
 EXVAE_API int exvae_upsample2x_nhwc_fwd(const float* x, int N, int H, int W, int C, float* y, exvae_stream_t stream);
 EXVAE_API int exvae_upsample2x_nhwc_bwd(const float* dy, int N, int H, int W, int C, float* dx, exvae_stream_t stream);

@@ -535,9 +535,16 @@ def test_cpu_tensor_is_rejected(ops):
         ops.pairwise_distance(torch.randn(3, 4), torch.randn(5, 4))
 
 
-# ------------------------------------------------------------------ K4 (conv = im2col + GEMM + col2im)
+# ------------------------------------------------------------------ K4 (implicit-GEMM conv; patch matrix for C < 16)
 @pytest.mark.parametrize("N,C,H,Cout,k,s,p", [(3, 1, 28, 32, 7, 1, 3), (2, 32, 14, 64, 5, 1, 2), (2, 32, 28, 32, 3, 2, 1),
-                                              (2, 64, 7, 6, 3, 1, 1), (2, 3, 8, 48, 3, 2, 1), (2, 64, 28, 1, 1, 1, 0)])
+                                              (2, 64, 7, 6, 3, 1, 1), (2, 3, 8, 48, 3, 2, 1), (2, 64, 28, 1, 1, 1, 0),
+                                              (5, 64, 28, 64, 3, 1, 1),     # convhvae decoder layer: implicit fwd + dx
+                                              (3, 64, 14, 64, 3, 2, 1),     # stride 2: implicit fwd, col2im dx
+                                              (3, 48, 16, 48, 3, 1, 1),     # single_conv block: 48 channels (2 k-blocks/tap)
+                                              (3, 96, 8, 96, 3, 1, 1), (2, 48, 16, 96, 3, 2, 1),
+                                              (7, 32, 7, 64, 3, 1, 1),      # 7x7 maps: two images per 128-row tile, odd N
+                                              (2, 96, 4, 2, 3, 1, 1),       # bottleneck head: 2 output channels
+                                              (1, 48, 32, 3, 3, 1, 1), (2, 2, 4, 96, 3, 1, 1)])
 def test_gated_conv2d_fwd_bwd(ops, N, C, H, Cout, k, s, p):
     F = torch.nn.functional
     g = torch.Generator().manual_seed(N + C + H + Cout + k)
@@ -557,9 +564,36 @@ def test_gated_conv2d_fwd_bwd(ops, N, C, H, Cout, k, s, p):
     close(xc.grad.permute(0, 3, 1, 2), ts[0].grad, rtol=1e-4, atol=1e-4)
     for c, t in zip(cs, ts[1:]):
         close(c.grad, t.grad, rtol=1e-4, atol=2e-4)
-    # plain conv + fused sigmoid
-    out2 = ops.conv2d(xc.detach(), cs[0].detach(), cs[1].detach(), s, p, 1)
-    close(out2.permute(0, 3, 1, 2), torch.sigmoid(F.conv2d(ts[0], ts[1], ts[2], stride=s, padding=p)), rtol=2e-5, atol=3e-5)
+    # plain conv + fused sigmoid, forward and backward
+    for t in ts:
+        t.grad = None
+    ref2 = torch.sigmoid(F.conv2d(ts[0], ts[1], ts[2], stride=s, padding=p))
+    ref2.backward(dout.double())
+    xc2 = xc.detach().clone().requires_grad_(True)
+    c2 = [cs[0].detach().clone().requires_grad_(True), cs[1].detach().clone().requires_grad_(True)]
+    out2 = ops.conv2d(xc2, c2[0], c2[1], s, p, 1)
+    close(out2.permute(0, 3, 1, 2), ref2, rtol=2e-5, atol=3e-5)
+    out2.backward(dout.permute(0, 2, 3, 1).contiguous().cuda())
+    close(xc2.grad.permute(0, 3, 1, 2), ts[0].grad, rtol=1e-4, atol=1e-4)
+    close(c2[0].grad, ts[1].grad, rtol=1e-4, atol=2e-4)
+    close(c2[1].grad, ts[2].grad, rtol=1e-4, atol=2e-4)
+
+
+def test_weight_norm_fwd_bwd(ops):
+    """torch.nn.utils.weight_norm(nn.Conv2d) (models/fully_conv.py:17): w = g v / ||v|| over each output channel."""
+    g_ = torch.Generator().manual_seed(4)
+    v = torch.randn(48, 16, 3, 3, generator=g_)
+    gg = torch.rand(48, 1, 1, 1, generator=g_) + 0.5
+    dw = torch.randn(48, 16, 3, 3, generator=g_)
+    vd, gd = v.double().requires_grad_(True), gg.double().requires_grad_(True)
+    w_ref = vd * (gd / vd.flatten(1).norm(dim=1).view(-1, 1, 1, 1))
+    w_ref.backward(dw.double())
+    vc, gc = v.cuda().requires_grad_(True), gg.cuda().requires_grad_(True)
+    w = ops.weight_norm(vc, gc)
+    close(w, w_ref, rtol=1e-5, atol=1e-6)
+    w.backward(dw.cuda())
+    close(vc.grad, vd.grad, rtol=1e-4, atol=1e-5)
+    close(gc.grad, gd.grad, rtol=1e-4, atol=1e-5)
 
 
 def test_elu_upsample(ops):
