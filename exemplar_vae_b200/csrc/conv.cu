@@ -21,62 +21,79 @@ namespace {
 
 inline int ew_blocks(long long n) { return (int)std::min<long long>((n + 255) / 256, 148LL * 32); }
 
-// col[m, (ky*kw + kx)*C + c] = x[n, oy*s + ky - p, ox*s + kx - p, c]   (0 outside the image)
+// col[m, (ky*kw + kx)*C + c] = x[n, oy*s + ky - p, ox*s + kx - p, c]   (0 outside the image); row pitch ldk >= kh*kw*C,
+// padding columns zero.  One thread per VW consecutive channels of one tap of one row (VW = 4 when C % 4 == 0), all
+// index arithmetic in 32 bits: the kernel is a pure gather and must run at HBM speed.
+template <int VW>
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const float* __restrict__ x, int N, int H, int W, int C,
                                                           int kh, int kw, int stride, int pad, int OH, int OW,
                                                           int ldk, float* __restrict__ col) {
+  const unsigned cv = (unsigned)(C / VW);                 // channel groups per tap
+  const unsigned per_row = (unsigned)(kh * kw) * cv;      // work items per row (the K padding is written by item 0)
+  const unsigned long long total = (unsigned long long)N * OH * OW * per_row;
   const int Kreal = kh * kw * C;
-  const long long K = ldk;                       // row pitch >= kh*kw*C (padding columns are zero)
-  const long long total = (long long)N * OH * OW * K;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const long long m = e / K;
-    const int k = (int)(e - m * K);
-    if (k >= Kreal) {
-      col[e] = 0.f;
-      continue;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned m = (unsigned)(e / per_row);
+    const unsigned it = (unsigned)(e - (unsigned long long)m * per_row);
+    const unsigned kk = it / cv, c = (it - kk * cv) * VW;
+    const unsigned ky = kk / (unsigned)kw, kx = kk - ky * (unsigned)kw;
+    const unsigned t = m / (unsigned)OW, ox = m - t * (unsigned)OW;
+    const unsigned n = t / (unsigned)OH, oy = t - n * (unsigned)OH;
+    const int iy = (int)oy * stride + (int)ky - pad, ix = (int)ox * stride + (int)kx - pad;
+    float* dst = col + (size_t)m * ldk + kk * C + c;
+    const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const float* src = x + (((size_t)n * H + iy) * W + ix) * C + c;
+    if (VW == 4) {
+      *reinterpret_cast<float4*>(dst) = in ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      *dst = in ? *src : 0.f;
     }
-    const int c = k % C, kk = k / C;
-    const int kx = kk % kw, ky = kk / kw;
-    const int ox = (int)(m % OW);
-    const long long t = m / OW;
-    const int oy = (int)(t % OH), n = (int)(t / OH);
-    const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)n * H + iy) * W + ix) * C + c];
-    col[e] = v;
+    if (it == 0)
+      for (int k = Kreal; k < ldk; ++k) col[(size_t)m * ldk + k] = 0.f;
   }
 }
 
-// dx[n, iy, ix, c] = sum over (ky,kx) with (iy + p - ky) % s == 0 ... of dcol[m(n,oy,ox), (ky*kw+kx)*C + c]
+// dx[n, iy, ix, c] = sum over the taps (ky,kx) with (iy + p - ky) % s == 0, ... of dcol[m(n,oy,ox), (ky*kw+kx)*C + c]
+// (gather form of the adjoint: no atomics, deterministic); one thread per VW channels of one input pixel
+template <int VW>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restrict__ dcol, int N, int H, int W, int C,
                                                           int kh, int kw, int stride, int pad, int OH, int OW,
                                                           int ldk, float* __restrict__ dx) {
-  const long long K = ldk;
-  const long long total = (long long)N * H * W * C;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % C);
-    long long t = e / C;
-    const int ix = (int)(t % W);
-    t /= W;
-    const int iy = (int)(t % H), n = (int)(t / H);
-    float a = 0.f;
+  const unsigned cv = (unsigned)(C / VW);
+  const unsigned long long total = (unsigned long long)N * H * W * cv;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned pix = (unsigned)(e / cv);
+    const unsigned c = (unsigned)(e - (unsigned long long)pix * cv) * VW;
+    const unsigned t = pix / (unsigned)W, ix = pix - t * (unsigned)W;
+    const unsigned n = t / (unsigned)H, iy = t - n * (unsigned)H;
+    float a[VW];
+#pragma unroll
+    for (int k = 0; k < VW; ++k) a[k] = 0.f;
     for (int ky = 0; ky < kh; ++ky) {
-      const int ty = iy + pad - ky;
+      const int ty = (int)iy + pad - ky;
       if (ty < 0 || ty % stride) continue;
       const int oy = ty / stride;
       if (oy >= OH) continue;
       for (int kx = 0; kx < kw; ++kx) {
-        const int tx = ix + pad - kx;
+        const int tx = (int)ix + pad - kx;
         if (tx < 0 || tx % stride) continue;
         const int ox = tx / stride;
         if (ox >= OW) continue;
-        const long long m = ((long long)n * OH + oy) * OW + ox;
-        a += dcol[m * K + (long long)(ky * kw + kx) * C + c];
+        const size_t m = ((size_t)n * OH + oy) * OW + ox;
+        const float* src = dcol + m * ldk + (ky * kw + kx) * C + c;
+        if (VW == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src);
+          a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        } else {
+          a[0] += *src;
+        }
       }
     }
-    dx[e] = a;
+    float* dst = dx + (size_t)pix * C + c;
+    if (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+    else *dst = a[0];
   }
 }
 
@@ -112,19 +129,19 @@ __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __r
                                                                 float* __restrict__ db0, float* __restrict__ db1,
                                                                 int accumulate) {
   if ((int)blockIdx.x < nred) {
-    const int per = Cin * KH * KW;
-    const int total = ncat * per;
+    // walk the PACKED layout (coalesced reads of the split-K partials); the scattered writes hit the small filter tensor
+    const int taps = KH * KW, per = Cin * taps;
+    const int total = ncat * taps * Cin;
     const size_t plane = (size_t)ncat * Kp;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nred * blockDim.x) {
-      const int co = e / per;
-      int r = e - co * per;
-      const int kw = r % KW;
-      r /= KW;
-      const int kh = r % KH, ci = r / KH;
-      const size_t src = (size_t)co * Kp + (kh * KW + kw) * cpad + ci;
+      const int ci = e % Cin;
+      const int r = e / Cin;
+      const int t = r % taps, co = r / taps;
+      const size_t src = (size_t)co * Kp + t * cpad + ci;
       float a = 0.f;
       for (int s = 0; s < S; ++s) a += part[(size_t)s * plane + src];
-      float* dst = co < oseg ? dW0 + (size_t)co * per + (e - co * per) : dW1 + (size_t)(co - oseg) * per + (e - co * per);
+      const int o = ci * taps + t;                          // [ci][kh][kw] inside one filter
+      float* dst = co < oseg ? dW0 + (size_t)co * per + o : dW1 + (size_t)(co - oseg) * per + o;
       *dst = accumulate ? *dst + a : a;
     }
     return;
@@ -187,15 +204,21 @@ __global__ void __launch_bounds__(256) up2_bwd_kernel(const float* __restrict__ 
 
 int conv_im2col(const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int OH, int OW, int ldk,
                 float* col, cudaStream_t st) {
-  const long long total = (long long)N * OH * OW * ldk;
-  im2col_nhwc_kernel<<<ew_blocks(total), 256, 0, st>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW, ldk, col);
+  const bool v4 = C % 4 == 0 && ldk % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(col) & 15) == 0;
+  const long long total = (long long)N * OH * OW * kh * kw * (C / (v4 ? 4 : 1));
+  if (v4) im2col_nhwc_kernel<4><<<ew_blocks(total), 256, 0, st>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW, ldk, col);
+  else im2col_nhwc_kernel<1><<<ew_blocks(total), 256, 0, st>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW, ldk, col);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
 int conv_col2im(const float* dcol, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int OH, int OW,
                 int ldk, float* dx, cudaStream_t st) {
-  const long long total = (long long)N * H * W * C;
-  col2im_nhwc_kernel<<<ew_blocks(total), 256, 0, st>>>(dcol, N, H, W, C, kh, kw, stride, pad, OH, OW, ldk, dx);
+  const bool v4 = C % 4 == 0 && ldk % 4 == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dcol) & 15) == 0;
+  const long long total = (long long)N * H * W * (C / (v4 ? 4 : 1));
+  if (v4) col2im_nhwc_kernel<4><<<ew_blocks(total), 256, 0, st>>>(dcol, N, H, W, C, kh, kw, stride, pad, OH, OW, ldk, dx);
+  else col2im_nhwc_kernel<1><<<ew_blocks(total), 256, 0, st>>>(dcol, N, H, W, C, kh, kw, stride, pad, OH, OW, ldk, dx);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EXVAE_OK : (int)e;
 }
@@ -229,10 +252,7 @@ extern "C" int exvae_im2col_nhwc(const float* x, int N, int H, int W, int C, int
   EXVAE_CHECK_ARG(x && col && N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0);
   const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
   EXVAE_CHECK_ARG(OH > 0 && OW > 0);
-  const long long total = (long long)N * OH * OW * kh * kw * C;
-  im2col_nhwc_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW,
-                                                                      kh * kw * C, col);
-  EXVAE_RETURN_LAST_ERROR();
+  return conv_im2col(x, N, H, W, C, kh, kw, stride, pad, OH, OW, kh * kw * C, col, as_stream(stream));
 }
 
 extern "C" int exvae_col2im_nhwc(const float* dcol, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
@@ -240,10 +260,7 @@ extern "C" int exvae_col2im_nhwc(const float* dcol, int N, int H, int W, int C, 
   EXVAE_CHECK_ARG(dcol && dx && N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0);
   const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
   EXVAE_CHECK_ARG(OH > 0 && OW > 0);
-  const long long total = (long long)N * H * W * C;
-  col2im_nhwc_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(dcol, N, H, W, C, kh, kw, stride, pad, OH, OW,
-                                                                      kh * kw * C, dx);
-  EXVAE_RETURN_LAST_ERROR();
+  return conv_col2im(dcol, N, H, W, C, kh, kw, stride, pad, OH, OW, kh * kw * C, dx, as_stream(stream));
 }
 
 extern "C" int exvae_elu_fwd(const float* x, int64_t n, float* y, exvae_stream_t stream) {

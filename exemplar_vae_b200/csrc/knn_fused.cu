@@ -192,54 +192,85 @@ __global__ void __launch_bounds__(256) knn_fused_kernel(const float* __restrict_
   }
 }
 
-// Merge the per-split lists: one warp per row over nsplit*k candidates keyed by (dist, global position); pass p picks
-// the smallest key strictly greater than pick p-1 (all loads of a pass are independent).
+// Merge the per-split lists (each sorted ascending): one warp per row, a k-way merge over the list HEADS.  Lane l owns
+// the splits l, l+32, ... (<= 8 of them: nsplit <= 256) and keeps their current heads in registers; every pass takes
+// the warp-wide smallest (dist, global position) head and only the owning lane loads that split's next entry.
 __global__ void __launch_bounds__(256) knn_fused_merge_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dist,
                                                               int G, int B, int k, int64_t* __restrict__ out_idx,
                                                               float* __restrict__ out_dist) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
-  const int n = G * k;
-  float lv = -INFINITY;
-  long long li = -1;
+  float hv[8];
+  long long hi[8];
+  int hp[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int g = lane + 32 * q;
+    hv[q] = INFINITY;
+    hi[q] = INT64_MAX;
+    hp[q] = 0;
+    if (g < G) {
+      const size_t o = ((size_t)g * B + b) * k;
+      const long long i = idx[o];
+      if (i >= 0) {
+        hv[q] = dist[o];
+        hi[q] = i;
+      }
+    }
+  }
   for (int p = 0; p < k; ++p) {
     float bv = INFINITY;
     long long bi = INT64_MAX;
-    for (int c = lane; c < n; c += 32) {
-      const int g = c / k, j = c - g * k;
-      const size_t o = ((size_t)g * B + b) * k + j;
-      const float v = dist[o];
-      const long long i = idx[o];
-      if (i < 0) continue;
-      const bool after = (v > lv) || (v == lv && i > li);
-      if (after && (v < bv || (v == bv && i < bi))) {
-        bv = v;
-        bi = i;
+    int bq = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (hv[q] < bv || (hv[q] == bv && hi[q] < bi)) {
+        bv = hv[q];
+        bi = hi[q];
+        bq = q;
       }
-    }
+    float wv = bv;
+    long long wi = bi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov < bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ov < wv || (ov == wv && oi < wi)) {
+        wv = ov;
+        wi = oi;
       }
     }
     if (lane == 0) {
-      out_idx[(size_t)b * k + p] = bi == INT64_MAX ? -1 : bi;
-      out_dist[(size_t)b * k + p] = bv;
+      out_idx[(size_t)b * k + p] = wi == INT64_MAX ? -1 : wi;
+      out_dist[(size_t)b * k + p] = wv;
     }
-    lv = bv;
-    li = bi;
+    if (wi != INT64_MAX && wi == bi && wv == bv) {       // this lane owns the winner (global positions are unique): advance
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q == bq) {
+          const int g = lane + 32 * q;
+          const int np = hp[q] + 1;
+          hp[q] = np;
+          hv[q] = INFINITY;
+          hi[q] = INT64_MAX;
+          if (np < k) {
+            const size_t o = ((size_t)g * B + b) * k + np;
+            const long long i = idx[o];
+            if (i >= 0) {
+              hv[q] = dist[o];
+              hi[q] = i;
+            }
+          }
+        }
+    }
   }
 }
 
 inline int knn_splits(int B, int C) {
   const int rb = ceil_div(B, KF_T);
   const int ntile = ceil_div(C, KF_T);
-  return std::max(1, std::min(ntile, ceil_div(sm_count(), rb)));
+  return std::max(1, std::min(std::min(ntile, 256), ceil_div(sm_count(), rb)));
 }
 
 struct KnnWs {

@@ -31,19 +31,35 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class FlatGrads:
-    """All parameter gradients as views of ONE contiguous buffer: a single all-reduce averages them,
-    and the buffer keeps gradient pointers stable for the fused optimizer / CUDA graphs."""
+    """All parameter gradients as views of ONE contiguous buffer: a few all-reduces average them, and the buffer
+    keeps gradient pointers stable for the fused optimizer / CUDA graphs.  The parameters are split into
+    ``n_buckets`` contiguous ranges (by size, in registration order); every range starts at a multiple of ``align``
+    floats and is padded to one (the multimem all-reduce needs 16-byte aligned slices per rank), the gaps stay zero.
+    ``alloc(n)`` may supply the storage (a region of the symmetric-memory arena)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], n_buckets: int = 1, align: int = 1, alloc=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
+        target = max(1, total // max(n_buckets, 1))
+        up = lambda v: (v + align - 1) // align * align
+        offsets, self.ranges, self.bucket_of = [], [], {}
+        off, lo, acc = 0, 0, 0
+        for i, p in enumerate(self.params):
+            offsets.append(off)
+            self.bucket_of[i] = len(self.ranges)
+            off += p.numel()
+            acc += p.numel()
+            if acc >= target and len(self.ranges) < n_buckets - 1 and i + 1 < len(self.params):
+                off = up(off)
+                self.ranges.append((lo, off))
+                lo, acc = off, 0
+        off = up(off)
+        self.ranges.append((lo, off))
         ref = self.params[0]
-        self.buf = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.buf[off:off + n].view_as(p)
-            off += n
+        self.buf = alloc(off) if alloc is not None else torch.zeros(off, dtype=ref.dtype, device=ref.device)
+        self.buf.zero_()
+        for p, o in zip(self.params, offsets):
+            p.grad = self.buf[o:o + p.numel()].view_as(p)
 
     def zero_(self):
         if self.buf.is_cuda:
@@ -58,6 +74,108 @@ class FlatGrads:
         self.buf.mul_(1.0 / world)
 
 
+class McComm:
+    """The symmetric-memory arena of one process group and the exvae multimem exchange kernels (csrc/mc_coll.cu):
+    all-reduce / all-gather / reduce-scatter as single kernels over NVLink / NVSwitch multicast instead of NCCL rings.
+    Regions are bump-allocated in the same order on every rank, so their offsets are symmetric."""
+
+    GRAD_CH0, GRAD_BLOCKS = 0, 16         # signal-pad channels of the gradient all-reduces (comm stream)
+    XCHG_CH0, XCHG_BLOCKS = 32, 4         # ... of the K1 exchanges (prior branch stream)
+
+    def __init__(self, group, device, arena_mb: int = 96):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.arena = symm.empty(arena_mb * (1 << 18), dtype=torch.float32, device=device)
+        self.arena.zero_()
+        self.hdl = symm.rendezvous(self.arena, group)
+        if not self.hdl.has_multicast_support:
+            raise RuntimeError("no NVSwitch multicast support")
+        if self.hdl.signal_pad_size // 4 // self.world < self.XCHG_CH0 + self.XCHG_BLOCKS:
+            raise RuntimeError("signal pad too small")
+        self.mc_base = int(self.hdl.multicast_ptr)
+        self.pads = int(self.hdl.signal_pad_ptrs_dev)
+        self.off = 0
+        self.regions = {}
+        self._stream = None
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    def region(self, name: str, n: int):
+        """(tensor view, offset in floats) of a named region of n floats (allocated once per (name, n))."""
+        key = (name, int(n))
+        ent = self.regions.get(key)
+        if ent is None:
+            lo = self.off
+            self.off = (lo + int(n) + 63) // 64 * 64
+            if self.off > self.arena.numel():
+                raise RuntimeError("symmetric arena exhausted")
+            ent = self.regions[key] = (self.arena[lo:lo + int(n)], lo)
+        return ent
+
+    def comm_stream(self):
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        return self._stream
+
+    def _s(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def all_reduce_(self, off: int, n: int, scale: float):
+        from ._lib import lib
+        L = lib()
+        L.check(L.exvae_mc_allreduce(self.mc_base + 4 * off, self.pads, n, self.rank, self.world, self.GRAD_CH0,
+                                     self.GRAD_BLOCKS, scale, self._s()), "mc_allreduce")
+
+    def all_gather(self, src: torch.Tensor, name: str) -> torch.Tensor:
+        """src (contiguous, a multiple of 16 bytes) -> [world, *src.shape] in the arena, identical on every rank."""
+        from ._lib import lib
+        L = lib()
+        n = src.numel() * src.element_size() // 4
+        view, off = self.region(name, n * self.world)
+        L.check(L.exvae_mc_allgather(src.data_ptr(), self.mc_base + 4 * off, self.pads, n, self.rank, self.world,
+                                     self.XCHG_CH0, self.XCHG_BLOCKS, self._s()), "mc_allgather")
+        return view.view(src.dtype).view(self.world, *src.shape)
+
+    def reduce_scatter(self, region_off: int, out: torch.Tensor):
+        """out = sum over ranks of slice ``rank`` of the [world][out.numel()] region at ``region_off``."""
+        from ._lib import lib
+        L = lib()
+        L.check(L.exvae_mc_reduce_scatter(self.mc_base + 4 * region_off, out.data_ptr(), self.pads, out.numel(),
+                                          self.rank, self.world, self.XCHG_CH0, self.XCHG_BLOCKS, self._s()),
+                "mc_reduce_scatter")
+        return out
+
+
+_MC = {}
+
+
+def mc_comm(group):
+    """The McComm of ``group`` (None when the multimem path is unavailable or disabled with EXVAE_MC=0)."""
+    return _MC.get(id(group))
+
+
+def _make_mc(group, device):
+    import os
+    if os.environ.get("EXVAE_MC", "1") == "0" or dist.get_backend(group) != "nccl":
+        return None
+    if id(group) in _MC:
+        return _MC[id(group)]
+    ok = torch.ones(1, device=device)
+    comm = None
+    try:
+        comm = McComm(group, device)
+    except Exception as ex:                      # no multicast / symmetric memory on this box: NCCL collectives
+        ok.zero_()
+        if dist.get_rank(group) == 0:
+            print(f"[exvae] multimem exchanges unavailable ({ex}); using NCCL", flush=True)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)        # all ranks or none
+    if ok.item() == 0:
+        comm = None
+    _MC[id(group)] = comm
+    return comm
+
+
 class GradBuckets:
     """Data-parallel gradient averaging in a few contiguous buckets of the flat buffer, each all-reduced
     (NCCL AVG, asynchronously on the communicator's stream) as soon as the backward has produced every
@@ -66,22 +184,12 @@ class GradBuckets:
     produces the last layers first); the bucket that holds the first-registered parameters completes last and
     is issued by ``finish()``, on the caller's stream after ``backward()`` has joined every side stream."""
 
-    def __init__(self, flat: FlatGrads, group=None, n_buckets: int = 3):
+    def __init__(self, flat: FlatGrads, group=None, comm=None, arena_off: int = 0):
         self.flat, self.group = flat, group
+        self.comm, self.arena_off = comm, arena_off      # multimem path: flat.buf is the arena region at arena_off
         self._avg = dist.get_backend(group) == "nccl"      # gloo (CPU tests) has no AVG: sum, then scale in finish()
-        total = flat.buf.numel()
-        target = max(1, total // n_buckets)
-        self.ranges, self.bucket_of = [], {}
-        off, lo, acc = 0, 0, 0
-        for i, p in enumerate(flat.params):
-            n = p.numel()
-            self.bucket_of[p.grad.data_ptr()] = len(self.ranges)
-            off += n
-            acc += n
-            if acc >= target and len(self.ranges) < n_buckets - 1 and i + 1 < len(flat.params):
-                self.ranges.append((lo, off))
-                lo, acc = off, 0
-        self.ranges.append((lo, off))
+        self.ranges = list(flat.ranges)
+        self.bucket_of = {p.grad.data_ptr(): flat.bucket_of[i] for i, p in enumerate(flat.params)}
         self.totals = [0] * len(self.ranges)
         for b in self.bucket_of.values():
             self.totals[b] += 1
@@ -102,6 +210,14 @@ class GradBuckets:
     def _fire(self, b):
         lo, hi = self.ranges[b]
         self.fired[b] = True
+        if self.comm is not None:
+            # one multimem kernel on the communication stream: rank r reduces slice r in the switch and multicasts it
+            cur, cs = torch.cuda.current_stream(), self.comm.comm_stream()
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                self.comm.all_reduce_(self.arena_off + lo, hi - lo, 1.0 / self.comm.world)
+                self.works.append(cs.record_event())
+            return
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self.works.append(dist.all_reduce(self.flat.buf[lo:hi], op=op, group=self.group, async_op=True))
 
@@ -121,7 +237,10 @@ class GradBuckets:
             if not self.fired[b]:
                 self._fire(b)
         for w in self.works:
-            w.wait()
+            if self.comm is not None:
+                torch.cuda.current_stream().wait_event(w)
+            else:
+                w.wait()
         if not self._avg:
             self.flat.buf.mul_(1.0 / dist.get_world_size(self.group))
         self.reset()
@@ -140,12 +259,23 @@ def shard_bank(model, optimizer=None, group=None, shard=True):
     # identical initial weights on every rank
     for p in model.parameters():
         dist.broadcast(p.data, src=0, group=group)
-    model.flat_grads = FlatGrads(model.parameters())
     import os
+    dev = next(model.parameters()).device
+    comm = _make_mc(group, dev) if dev.type == "cuda" else None
+    model.mc_comm = comm
     if os.environ.get("EXVAE_GRAD_SYNC", "buckets") == "single":      # one blocking all-reduce after the backward
+        model.flat_grads = FlatGrads(model.parameters())
         model.grad_sync = lambda: model.flat_grads.all_reduce_mean(group)
         return model
-    buckets = GradBuckets(model.flat_grads, group)
+    arena_off = 0
+    if comm is not None:
+        total = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        cap = total + 3 * 4 * world * 16
+        view, arena_off = comm.region(f"grads{id(model)}", cap)
+        model.flat_grads = FlatGrads(model.parameters(), n_buckets=3, align=4 * world, alloc=lambda n: view[:n])
+    else:
+        model.flat_grads = FlatGrads(model.parameters(), n_buckets=3)
+    buckets = GradBuckets(model.flat_grads, group, comm, arena_off)
     model.grad_buckets = buckets
     from . import ops
     ops.set_grad_ready_hook(buckets.ready)       # dense layers report their in-kernel accumulated gradients

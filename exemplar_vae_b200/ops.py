@@ -988,45 +988,62 @@ class _PriorLSESharded(torch.autograd.Function):
     latents (+indices), run K1 for ALL rows against the LOCAL shard, all-gather the [B_total,4]
     partial statistics (the single LSE exchange) and merge.  Backward: all-gather the row grads,
     run the K1 backward against the local shard (dmu is complete for the shard), reduce-scatter
-    the partial dz back to the row owners."""
+    the partial dz back to the row owners.
+
+    The exchanges are single multimem kernels over the NVSwitch multicast mapping of a symmetric arena
+    (distributed.McComm, csrc/mc_coll.cu) when the box supports it, else NCCL collectives."""
 
     @staticmethod
     def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group):
         import torch.distributed as dist
+        from .distributed import mc_comm
         L = lib()
         z, mu, logvar = _f32(z, "z"), _f32(mu, "mu"), _f32(logvar, "logvar")
         G, rank = dist.get_world_size(group), dist.get_rank(group)
         B, D = z.shape
         C = mu.shape[0]
         masked = z_idx is not None and mu_idx is not None
-        z_all = torch.empty((G * B, D), dtype=torch.float32, device=z.device)
+        comm = mc_comm(group)
+        if comm is not None and ((B * D) % 4 or B % 4):
+            comm = None                                    # the multimem kernels move 16-byte units
         zi_all = None
         if masked:
             z_idx = _i64(z_idx).reshape(-1)
             mu_idx = _i64(mu_idx).reshape(-1)
-            zi_all = torch.empty((G * B,), dtype=torch.int64, device=z.device)
-            # (torch's _coalescing_manager would make this one NCCL launch, but it breaks CUDA-graph capture:
-            #  "dependency created on uncaptured work in another stream", torch 2.11)
-            dist.all_gather_into_tensor(z_all, z, group=group)
-            dist.all_gather_into_tensor(zi_all, z_idx, group=group)
         else:
             mu_idx = None
+        if comm is not None:
+            z_all = comm.all_gather(z, "z").view(G * B, D)
+            if masked:
+                zi_all = comm.all_gather(z_idx, "zi").view(G * B)
+            _count(2 if masked else 1)
+        else:
+            z_all = torch.empty((G * B, D), dtype=torch.float32, device=z.device)
+            # (torch's _coalescing_manager would make the two gathers one NCCL launch, but it breaks CUDA-graph
+            #  capture: "dependency created on uncaptured work in another stream", torch 2.11)
             dist.all_gather_into_tensor(z_all, z, group=group)
+            if masked:
+                zi_all = torch.empty((G * B,), dtype=torch.int64, device=z.device)
+                dist.all_gather_into_tensor(zi_all, z_idx, group=group)
         Bt = G * B
         ws = _ws(L.exvae_prior_lse_workspace_bytes(Bt, C, D), z.device)
         stats = torch.empty((Bt, 4), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_fwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, None, _p(stats),
                                       _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
         _count(3)
-        all_stats = torch.empty((G, Bt, 4), dtype=torch.float32, device=z.device)
-        dist.all_gather_into_tensor(all_stats, stats, group=group)
+        if comm is not None:
+            all_stats = comm.all_gather(stats, "stats")             # the single LSE-partial exchange: one kernel
+            _count(1)
+        else:
+            all_stats = torch.empty((G, Bt, 4), dtype=torch.float32, device=z.device)
+            dist.all_gather_into_tensor(all_stats, stats, group=group)
         log_p = torch.empty((Bt,), dtype=torch.float32, device=z.device)
         lse2 = torch.empty((Bt,), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z_all), _p(logvar), Bt, D, int(c_total), None, _p(log_p),
                                            _p(lse2), _stream()), "prior_lse_finalize")
         _count(1)
         ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws)
-        ctx.meta = (B, Bt, C, D, G, rank, group)
+        ctx.meta = (B, Bt, C, D, G, rank, group, comm)
         return log_p[rank * B:(rank + 1) * B].clone()
 
     @staticmethod
@@ -1034,19 +1051,28 @@ class _PriorLSESharded(torch.autograd.Function):
         import torch.distributed as dist
         L = lib()
         z_all, mu, logvar, zi_all, mu_idx, lse2, ws = ctx.saved_tensors
-        B, Bt, C, D, G, rank, group = ctx.meta
+        B, Bt, C, D, G, rank, group, comm = ctx.meta
         g = _f32(g, "grad")
-        g_all = torch.empty((Bt,), dtype=torch.float32, device=g.device)
-        dist.all_gather_into_tensor(g_all, g, group=group)
-        dz_all = torch.empty_like(z_all)
         dmu = torch.empty_like(mu)
         dlv = torch.empty((D,), dtype=torch.float32, device=g.device)
+        dz = torch.empty((B, D), dtype=torch.float32, device=g.device)
+        if comm is not None:
+            g_all = comm.all_gather(g, "g").view(Bt)
+            dz_all, dz_off = comm.region("dz", Bt * D)               # K1 writes its partial dz straight into the arena
+            dz_all = dz_all.view(Bt, D)
+        else:
+            g_all = torch.empty((Bt,), dtype=torch.float32, device=g.device)
+            dist.all_gather_into_tensor(g_all, g, group=group)
+            dz_all = torch.empty_like(z_all)
         L.check(L.exvae_prior_lse_bwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(lse2),
                                       _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, None, _stream()),
                 "prior_lse_bwd")
         _count(3)
-        dz = torch.empty((B, D), dtype=torch.float32, device=g.device)
-        dist.reduce_scatter_tensor(dz, dz_all, op=dist.ReduceOp.SUM, group=group)
+        if comm is not None:
+            comm.reduce_scatter(dz_off, dz)                          # sum over the shards, reduced in the switch
+            _count(2)
+        else:
+            dist.reduce_scatter_tensor(dz, dz_all, op=dist.ReduceOp.SUM, group=group)
         return dz, dmu, dlv.view_as(logvar), None, None, None, None
 
 

@@ -292,6 +292,23 @@ EXVAE_API int exvae_lincomb4(const float* x0, const float* x1, const float* x2, 
 EXVAE_API int exvae_elbo_reduce_bwd(const float* g3, const float* g_loss_b, int B, float beta, const float* beta_dev,
                                     int average, float* dRE, float* dKL, exvae_stream_t stream);
 
+/* ---------------------------------------------------------------- NVLink / NVSwitch exchanges (multi-GPU)
+ * The reference is single-device.  The exchanges of the range-sharded step run over SYMMETRIC memory (one buffer per
+ * rank with the same layout, mapped into every peer and into one NVSwitch multicast address; set up by the host with
+ * torch.distributed._symmetric_memory): mc_ptr arguments are MULTICAST addresses (multimem.st = one store lands in all
+ * GPUs, multimem.ld_reduce = the sum over all GPUs computed in the switch), signal_pads_dev is the device array of
+ * the ranks' signal pads ([channel][world] uint32 flags) used by the in-kernel barrier.  Each launch uses channels
+ * [channel0, channel0 + blocks), blocks <= max_blocks; launches that may run concurrently need disjoint channels.
+ *   allreduce      in place over n floats of the buffer (n % (4*world) == 0): buffer = scale * sum over ranks
+ *   allgather      src (local, n floats) -> slot `rank` of the [world][n] region mc_dst, on every rank
+ *   reduce_scatter out (local, n floats) = sum over ranks of slice `rank` of the [world][n] region mc_src            */
+EXVAE_API int exvae_mc_allreduce(float* mc_ptr, void* signal_pads_dev, int64_t n, int rank, int world, int channel0,
+                                 int max_blocks, float scale, exvae_stream_t stream);
+EXVAE_API int exvae_mc_allgather(const float* src, float* mc_dst, void* signal_pads_dev, int64_t n, int rank, int world,
+                                 int channel0, int max_blocks, exvae_stream_t stream);
+EXVAE_API int exvae_mc_reduce_scatter(const float* mc_src, float* out, void* signal_pads_dev, int64_t n, int rank,
+                                      int world, int channel0, int max_blocks, exvae_stream_t stream);
+
 /* ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
  * Device-side replacements for torch.bernoulli (utils/training.py:31), torch.randint
  * (models/BaseModel.py:245,257) and normal_() (models/BaseModel.py:81).  `counter` is a device

@@ -52,10 +52,11 @@ def _worker(rank, world, port, ret):
     # bucketed, overlapped gradient averaging: gradients reported out of registration order, one never reported
     from exemplar_vae_b200.distributed import GradBuckets
     qs = [torch.nn.Parameter(torch.zeros(n)) for n in (7, 40, 3, 50, 20)]
-    fq = FlatGrads(qs)
-    gb = GradBuckets(fq, None, n_buckets=3)
+    fq = FlatGrads(qs, n_buckets=3, align=8)          # bucket starts / ends padded to 8 floats (multimem slices)
+    gb = GradBuckets(fq, None)
     spans = gb.ranges
-    ok4 = spans[0][0] == 0 and spans[-1][1] == 120 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    ok4 = (spans[0][0] == 0 and spans[-1][1] == fq.buf.numel() and len(spans) == 3
+           and all(a[1] == b[0] and a[1] % 8 == 0 for a, b in zip(spans, spans[1:])))
     for step in range(2):                                   # twice: the bucket state resets after finish()
         fq.zero_()
         for i, q in enumerate(qs):

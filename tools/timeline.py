@@ -16,7 +16,14 @@ def main():
     from exemplar_vae_b200.config import default_args
     sys.argv = [sys.argv[0]] + sys.argv[1:]
     a = bench.parse()
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     args = default_args(device="cuda", seed=0, **bench.model_kwargs(a))
     torch.manual_seed(0)
     model = E.importing_model(args)(args).to(dev)
@@ -24,6 +31,9 @@ def main():
     T = a.train_size
     dataset = torch.utils.data.TensorDataset(data, torch.arange(T).view(-1, 1), torch.zeros(T))
     opt = E.AdamNormGrad(model.parameters(), lr=5e-4)
+    if world > 1:
+        from exemplar_vae_b200 import distributed as D
+        D.shard_bank(model, opt, dist.group.WORLD, shard=not a.approximate)
     cache = None
     if a.approximate:
         with torch.no_grad():
@@ -40,6 +50,9 @@ def main():
         for _ in range(3):
             step.step(x, xi)
         torch.cuda.synchronize()
+    if rank != 0:
+        torch.cuda.synchronize()
+        os._exit(0)
     path = os.path.join(ROOT, "gpurun_out", "timeline_trace.json")
     prof.export_chrome_trace(path)
     ev = json.load(open(path))["traceEvents"]
@@ -71,6 +84,9 @@ def main():
         name = e["name"].replace("exvae::<unnamed>::", "").replace("void ", "")[:110]
         print(f"| {e['ts'] - t0:.1f} | {e['dur']:.1f} | {e.get('args', {}).get('stream', '?')} | `{name}` |")
     os.remove(path)
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
