@@ -352,35 +352,54 @@ __global__ void __launch_bounds__(256) prior_bwd_prep_kernel(const float* __rest
   }
 }
 
-// finish of a row-split pass 2: one CTA (128 threads = exemplar rows) per tile adds the splits in a fixed order,
+// finish of a row-split pass 2: one CTA (512 threads: 4 per exemplar row, each a quarter of the float4 chunks) per
+// tile of 128 rows adds the splits in a fixed order,
 //   dmu[n,d] = (G[n,d] - colsum_n ms[n,d]) / sigma_d ;  coldot_part[tile][d] = sum_n (G[n,d] - colsum_n ms[n,d]) ms[n,d]
-__global__ void __launch_bounds__(128) prior_bwd_cols_kernel(const float* __restrict__ gcol_part,
+__global__ void __launch_bounds__(512) prior_bwd_cols_kernel(const float* __restrict__ gcol_part,
                                                              const float* __restrict__ tot_part,
                                                              const float* __restrict__ ms,
                                                              const float* __restrict__ isig, int rsplit, int C, int D,
                                                              int LD, int NG, int Cpad, float* __restrict__ dmu,
                                                              float* __restrict__ coldot_part) {
-  __shared__ float red[4][132];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = blockIdx.x * 128 + tid;
+  extern __shared__ float pdm[];            // [128][NG + 1] products dms * ms
+  const int tid = threadIdx.x;
+  const int r = tid >> 2, q = tid & 3;
+  const int n = blockIdx.x * 128 + r;
+  const int P = NG + 1;
   float tot = 0.f;
   for (int s = 0; s < rsplit; ++s) tot += tot_part[(size_t)s * Cpad + n];
-  for (int d = 0; d < LD; ++d) {
-    float pd = 0.f;
-    if (d < D) {
-      float g = 0.f;
-      for (int s = 0; s < rsplit; ++s) g += gcol_part[((size_t)s * Cpad + n) * NG + d];
-      const float mv = ms[(size_t)n * LD + d];
-      const float dv = g - tot * mv;
-      if (n < C) dmu[(size_t)n * D + d] = dv * isig[d];
-      pd = dv * mv;
+  for (int c4 = q; c4 < NG / 4; c4 += 4) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < rsplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(gcol_part + ((size_t)s * Cpad + n) * NG + 4 * c4);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }
-    pd = warp_sum(pd);
-    if (lane == 0) red[warp][d] = pd;
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = 4 * c4 + e;
+      float pd = 0.f;
+      if (d < D) {
+        const float mv = ms[(size_t)n * LD + d];
+        const float dv = gv[e] - tot * mv;
+        if (n < C) dmu[(size_t)n * D + d] = dv * isig[d];
+        pd = dv * mv;
+      }
+      pdm[r * P + d] = pd;
+    }
   }
   __syncthreads();
-  for (int d = tid; d < LD; d += 128)
-    coldot_part[(size_t)blockIdx.x * LD + d] = d < D ? (red[0][d] + red[1][d]) + (red[2][d] + red[3][d]) : 0.f;
+  // column sums over the 128 rows: 4 row groups x NG columns, then the 4 partials in a fixed order
+  float* cd = pdm + 128 * P;                // [4][NG]
+  for (int e = tid; e < 4 * NG; e += 512) {
+    const int d = e % NG, rg = e / NG;
+    float a = 0.f;
+    for (int rr = 0; rr < 32; ++rr) a += pdm[(rg * 32 + rr) * P + d];
+    cd[rg * NG + d] = a;
+  }
+  __syncthreads();
+  for (int d = tid; d < LD; d += 512)
+    coldot_part[(size_t)blockIdx.x * LD + d] = d < D ? (cd[d] + cd[NG + d]) + (cd[2 * NG + d] + cd[3 * NG + d]) : 0.f;
 }
 
 }  // namespace
@@ -441,8 +460,8 @@ int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out
   rc = a.zip ? launch(prior_bwd_tc_kernel<true, true>, dim3(ntile, rsplit), mm, mz, mzt)
              : launch(prior_bwd_tc_kernel<true, false>, dim3(ntile, rsplit), mm, mz, mzt);
   if (rc || rsplit == 1) return rc;
-  if (a.LD > 132) return EXVAE_ERR_UNSUPPORTED;
-  prior_bwd_cols_kernel<<<ntile, 128, 0, st>>>(a.gcol_part, a.tot_part, a.ms, a.isig, rsplit, a.C, a.D, a.LD, a.NG, a.Cpad,
+  const size_t sh = sizeof(float) * (128 * (a.NG + 1) + 4 * a.NG);
+  prior_bwd_cols_kernel<<<ntile, 512, sh, st>>>(a.gcol_part, a.tot_part, a.ms, a.isig, rsplit, a.C, a.D, a.LD, a.NG, a.Cpad,
                                                a.dmu, a.coldot_part);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EXVAE_OK : (int)e;
