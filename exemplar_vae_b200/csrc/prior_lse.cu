@@ -757,6 +757,32 @@ __global__ void __launch_bounds__(256) prior_bwd_rows_kernel(const float* __rest
   if (tid == 0) rs[b] = rtot;
 }
 
+// the same for a handful of partials per row (tensor-core path: one per column split): one WARP per row, lanes over d
+__global__ void __launch_bounds__(256) prior_bwd_rows_small_kernel(const float* __restrict__ dzs_part,
+                                                                   const float* __restrict__ rowsum_part,
+                                                                   const float* __restrict__ zs,
+                                                                   const float* __restrict__ isig, int npart, int B,
+                                                                   int D, int LD, int Bpad, float* __restrict__ dz,
+                                                                   float* __restrict__ rowdot, float* __restrict__ rs) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float rtot = 0.f;
+  for (int t = 0; t < npart; ++t) rtot += rowsum_part[(size_t)t * Bpad + b];
+  for (int d = lane; d < LD; d += 32) {
+    float rd = 0.f;
+    if (d < D) {
+      float acc = 0.f;
+      for (int t = 0; t < npart; ++t) acc += dzs_part[((size_t)t * Bpad + b) * LD + d];
+      const float zv = zs[(size_t)b * LD + d];
+      const float dzs = acc - zv * rtot;
+      dz[(size_t)b * D + d] = dzs * isig[d];
+      rd = dzs * zv;
+    }
+    rowdot[(size_t)b * LD + d] = rd;
+  }
+  if (lane == 0) rs[b] = rtot;
+}
+
 // dlogvar[d] = -0.5 * ( sum_b rs[b] + sum_b rowdot[b,d] + sum_tile coldot_part[tile,d] ): one block per dimension
 __global__ void __launch_bounds__(256) prior_bwd_dlogvar_kernel(const float* __restrict__ rs,
                                                                 const float* __restrict__ rowdot,
@@ -1052,8 +1078,12 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
     int nsplit = 0, ntile = 0;
     rc = prior_bwd_tc_launch(a, &nsplit, &ntile, st);
     if (rc) return rc;
-    prior_bwd_rows_kernel<<<B, 256, (8 * w.LD + 8) * sizeof(float), st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, nsplit, B,
-                                                                         D, w.LD, w.Bpad, dz, w.rowdot, w.rs);
+    if (nsplit <= 16)
+      prior_bwd_rows_small_kernel<<<ceil_div(B, 8), 256, 0, st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, nsplit, B, D, w.LD,
+                                                                  w.Bpad, dz, w.rowdot, w.rs);
+    else
+      prior_bwd_rows_kernel<<<B, 256, (8 * w.LD + 8) * sizeof(float), st>>>(w.dzs_part, w.rowsum_part, w.zs, w.isig, nsplit, B,
+                                                                           D, w.LD, w.Bpad, dz, w.rowdot, w.rs);
     EXVAE_CUDA(cudaGetLastError());
     prior_bwd_dlogvar_kernel<<<D, 256, 0, st>>>(w.rs, w.rowdot, w.coldot_part, B, ntile, D, w.LD, dlogvar);
     EXVAE_RETURN_LAST_ERROR();

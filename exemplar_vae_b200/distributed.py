@@ -37,22 +37,34 @@ class FlatGrads:
     floats and is padded to one (the multimem all-reduce needs 16-byte aligned slices per rank), the gaps stay zero.
     ``alloc(n)`` may supply the storage (a region of the symmetric-memory arena)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], n_buckets: int = 1, align: int = 1, alloc=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], n_buckets: int = 1, align: int = 1, alloc=None,
+                 groups=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        sizes = [p.numel() for p in self.params]
+        total = sum(sizes)
+        # bucket boundaries: walk the parameters from the LAST one (the backward produces those gradients first) and
+        # cut whenever a bucket has reached total / n_buckets -- but only between parameter GROUPS (`groups[i]` = id
+        # of the layer parameter i belongs to), so that no bucket waits for half a layer of the next one
+        groups = list(groups) if groups is not None else list(range(len(self.params)))
         target = max(1, total // max(n_buckets, 1))
+        cuts, acc = [], 0
+        for i in range(len(self.params) - 1, 0, -1):
+            acc += sizes[i]
+            if acc >= target and groups[i] != groups[i - 1] and len(cuts) < n_buckets - 1:
+                cuts.append(i)              # a new bucket starts at parameter i
+                acc = 0
+        cuts = sorted(cuts)
         up = lambda v: (v + align - 1) // align * align
         offsets, self.ranges, self.bucket_of = [], [], {}
-        off, lo, acc = 0, 0, 0
+        off, lo = 0, 0
         for i, p in enumerate(self.params):
-            offsets.append(off)
-            self.bucket_of[i] = len(self.ranges)
-            off += p.numel()
-            acc += p.numel()
-            if acc >= target and len(self.ranges) < n_buckets - 1 and i + 1 < len(self.params):
+            if i in cuts:
                 off = up(off)
                 self.ranges.append((lo, off))
-                lo, acc = off, 0
+                lo = off
+            offsets.append(off)
+            self.bucket_of[i] = len(self.ranges)
+            off += sizes[i]
         off = up(off)
         self.ranges.append((lo, off))
         ref = self.params[0]
@@ -246,6 +258,15 @@ class GradBuckets:
         self.reset()
 
 
+def _layer_groups(model):
+    """Layer id of every trainable parameter (first two components of its name: 'q_z_layers.0', 'p_x_mean.linear')."""
+    ids, out = {}, []
+    for name, p in model.named_parameters():
+        if p.requires_grad:
+            out.append(ids.setdefault(".".join(name.split(".")[:2]), len(ids)))
+    return out
+
+
 def shard_bank(model, optimizer=None, group=None, shard=True):
     """Switch ``model`` to a range-sharded exemplar bank + data-parallel gradients over ``group``.
     ``shard=False`` keeps the bank replicated (pure data parallelism: every rank draws all N exemplars /
@@ -272,9 +293,10 @@ def shard_bank(model, optimizer=None, group=None, shard=True):
         total = sum(p.numel() for p in model.parameters() if p.requires_grad)
         cap = total + 3 * 4 * world * 16
         view, arena_off = comm.region(f"grads{id(model)}", cap)
-        model.flat_grads = FlatGrads(model.parameters(), n_buckets=3, align=4 * world, alloc=lambda n: view[:n])
+        model.flat_grads = FlatGrads(model.parameters(), n_buckets=3, align=4 * world, alloc=lambda n: view[:n],
+                                     groups=_layer_groups(model))
     else:
-        model.flat_grads = FlatGrads(model.parameters(), n_buckets=3)
+        model.flat_grads = FlatGrads(model.parameters(), n_buckets=3, groups=_layer_groups(model))
     buckets = GradBuckets(model.flat_grads, group, comm, arena_off)
     model.grad_buckets = buckets
     from . import ops

@@ -57,6 +57,10 @@ def _worker(rank, world, port, ret):
     spans = gb.ranges
     ok4 = (spans[0][0] == 0 and spans[-1][1] == fq.buf.numel() and len(spans) == 3
            and all(a[1] == b[0] and a[1] % 8 == 0 for a, b in zip(spans, spans[1:])))
+    # layer-aware cuts: parameters 0-1 form one layer, 2-4 another -> a 2-bucket split may only cut between them
+    rs = [torch.nn.Parameter(torch.zeros(n)) for n in (7, 40, 3, 50, 20)]
+    fr = FlatGrads(rs, n_buckets=2, groups=[0, 0, 1, 1, 1])
+    ok4 = ok4 and fr.ranges == [(0, 47), (47, 120)] and [fr.bucket_of[i] for i in range(5)] == [0, 0, 1, 1, 1]
     for step in range(2):                                   # twice: the bucket state resets after finish()
         fq.zero_()
         for i, q in enumerate(qs):
