@@ -262,6 +262,14 @@ def dense_call_flops(name, args):
     if name == "exvae_linear_bwd":
         R, K, O = args[4:7]
         return 2.0 * R * K * O * (2 if args[10] else 1), (R, K, O)
+    if name in ("exvae_conv2d_fwd", "exvae_conv2d_bwd"):
+        # (x, w, b0, b1 | out, sig, dout, N, H, W, Cin, KH, KW, stride, pad, O, gated, ...): real (unpadded) contraction size
+        o = 4 if name == "exvae_conv2d_fwd" else 5
+        N, H, W, Cin, KH, KW, stride, pad, O, gated = args[o:o + 10]
+        OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+        R, K, ncat = N * OH * OW, KH * KW * Cin, (2 * O if gated else O)
+        mult = 1 if name == "exvae_conv2d_fwd" else (2 if args[o + 13] else 1)      # bwd: dW (+ dx when requested)
+        return 2.0 * R * K * ncat * mult, (R, K, ncat)
     return None, None
 
 
@@ -502,8 +510,8 @@ def run_gpu(a):
     ach_alg = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
     top = sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]
     roofline = {
-        "kernel": "gemm_tf32x3_kernel — every dense-layer C-ABI call of one step (gated_dense/linear fwd+bwd, incl. their "
-                  "staging/finish kernels): the dominant kernel of the step",
+        "kernel": "gemm_tf32x3_kernel — every dense-layer / convolution C-ABI call of one step (gated_dense, linear, conv2d "
+                  "fwd+bwd, incl. their staging/finish kernels): the dominant kernel of the step",
         "bound": "tensor",
         "achieved": 3.0 * ach_alg if ach_alg else None,
         "peak": tf32_peak, "unit": "TFLOP/s", "frac": (3.0 * ach_alg / tf32_peak) if ach_alg else None,

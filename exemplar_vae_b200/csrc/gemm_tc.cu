@@ -66,7 +66,23 @@ struct TcParams {
   unsigned long long* trace;   // debug: per-CTA {start, end, tiles, SM} (tools/gemm_trace.py), null in production
 };
 unsigned long long* g_trace = nullptr;
+// CTA-pair (cta_group::2) variant of the big forward GEMMs: EXVAE_GEMM_PAIR=0 disables it
+inline bool pair_enabled() {
+  static const bool on = [] { const char* e = getenv("EXVAE_GEMM_PAIR"); return !(e && strcmp(e, "0") == 0); }();
+  return on;
+}
 
+// debug (trace runs only): cycles spent inside a barrier wait
+template <typename F>
+__device__ __forceinline__ void timed_wait(bool on, long long& acc, F&& wait) {
+  if (on) {
+    const long long t0 = clock64();
+    wait();
+    acc += clock64() - t0;
+  } else {
+    wait();
+  }
+}
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -95,13 +111,14 @@ struct TileCoord {
   int mrows;            // rows of the 128-row tile that hold data (implicit conv tiles may be shorter)
   int cn0, coh0;        // implicit conv: first image / first output row of the tile
 };
-template <int BN, int EPI, bool B_MN_, int CONV = 0>
-__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
+template <int BN, int EPI, bool B_MN_, int CONV = 0, bool PAIR = false>
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int rank = 0) {
   TileCoord c;
   const int nt = t % p.ntn;
   const int rest = t / p.ntn;
-  const int mt = rest % p.ntm;
+  int mt = rest % p.ntm;
   c.z = rest / p.ntm;
+  if (PAIR) mt = 2 * mt + rank;          // CTA pair: a 256-row tile = two 128-row units, one per CTA
   c.m0 = mt * TBM;
   c.mrows = TBM;
   c.cn0 = c.coh0 = 0;
@@ -120,6 +137,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
   c.neff = c.last ? p.neff_last : BN;
   c.goff = c.last ? p.goff_last : BN / 2;
   c.bbytes = B_MN_ ? ((c.neff + 31) / 32) * 4096 : c.neff * 128;
+  if (PAIR) c.bbytes >>= 1;              // each CTA of a pair holds half of the B tile's rows
   c.kbeg = c.z * p.kchunk;
   const int kend = min(p.K, c.kbeg + p.kchunk);
   c.nkb = max(0, (kend - c.kbeg + TBK - 1) / TBK);
@@ -139,12 +157,19 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
 // is what bounds this kernel (measured: TMA-only 0.33, + conversion 0.59, + MMAs 0.91 us per k-block, additive;
 // profiles/r1_gemm_persistent.md).  A stage is 48 KB, so the ring has 4 of them.  An MN-major A tile needs no
 // swizzle (no MMA reads it): one {128 m, 32 k} box, column m read by lane m without bank conflicts.
-template <int BN, bool A_MN, bool B_MN, int EPI, int CONV = 0>
+//
+// PAIR: two CTAs of a cluster (one TPC) cooperate on a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA loads and
+// converts its own 128 rows of A (into its own TMEM) and HALF of the B tile's rows; the leader CTA issues M = 256 MMAs
+// that read A from both tensor memories and B from both shared memories and write each CTA's 128 accumulator rows.
+// The B operand is then staged, converted and read once per 256 output rows: 80 KB instead of 128 KB of shared-memory
+// traffic per k-block and SM, below the 0.39 us the MMAs themselves need.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CONV = 0, bool PAIR = false>
 __global__ void __launch_bounds__(TTHREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+  static_assert(!PAIR || (!A_MN && !B_MN && (EPI == TC_GATED || EPI == TC_BIAS_ACT)), "pair mode: K-major forward GEMMs");
   constexpr int A_BYTES = TBM * TBK * 4;   // 16 KB: raw A tile
-  constexpr int B_BYTES = BN * TBK * 4;    // raw (= hi) B tile; the lo tile follows it
+  constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TBK * 4;    // raw (= hi) B tile (this CTA's rows); the lo tile follows it
   constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   constexpr int B_OFF = A_BYTES;                         // B hi slot inside a stage
   // Exemplar-prior epilogues keep TWO accumulators per tile: the hi*hi products in one, the two small cross products
@@ -168,6 +193,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;          // 0 = leader of the pair
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // first tile / tile stride of this CTA (pair)
+  const int nct = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   unsigned long long* tr = p.trace ? p.trace + 8 * (size_t)blockIdx.x : nullptr;
   if (tr && tid == 0) tr[0] = gtimer();
 
@@ -175,19 +203,23 @@ __global__ void __launch_bounds__(TTHREADS, 1)
 #pragma unroll
     for (int s = 0; s < TSTAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], NCONV);
+      mbar_init(&conv[s], PAIR ? 2 * NCONV : NCONV);      // pair: the leader's barrier collects both CTAs' converters
       mbar_init(&empty[s], 1);
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], NEPI);
+      mbar_init(&acc_empty[a], PAIR ? 2 * NEPI : NEPI);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc2(tmem_slot, TM_COLS);
+    else tmem_alloc(tmem_slot, TM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // the peer's barriers exist before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -195,11 +227,12 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     // ---------------------------------------------------------------- TMA producer
     if (elect_one_sync()) {
       int it = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
+      long long w_prod = 0;
+      for (int t = cta0; t < p.ntiles; t += nct) {
+        const TileCoord c = tile_coord<BN, EPI, B_MN, CONV, PAIR>(p, t, rank);
         for (int kb = 0; kb < c.nkb; ++kb, ++it) {
           const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          timed_wait(tr != nullptr, w_prod, [&] { mbar_wait(&empty[s], ph ^ 1); });
           mbar_arrive_expect_tx(&full[s], (CONV ? c.mrows * 128 : A_BYTES) + c.bbytes);
           unsigned char* sa = smem + s * STAGE_BYTES;
           unsigned char* sb = sa + B_OFF;
@@ -215,7 +248,12 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           } else {
             tma_load_2d(sa, &tmA, &full[s], c.m0, k0);                        // box {128 m, 32 k}, no swizzle
           }
-          if (!B_MN) {
+          if (PAIR) {
+            // this CTA's half of the B tile's rows: gated = the h rows (leader) / the g rows (peer), else N/2 rows each
+            const CUtensorMap* mb = c.last ? &tmBl : &tmB;
+            if (EPI == TC_GATED) tma_load_2d(sb, mb, &full[s], k0, rank == 0 ? c.n0 : p.gated_O + c.n0);
+            else tma_load_2d(sb, mb, &full[s], k0, c.n0 + rank * (c.neff >> 1));
+          } else if (!B_MN) {
             const CUtensorMap* mb = c.last ? &tmBl : &tmB;                     // narrow last tile: smaller boxes
             if (EPI == TC_GATED) {                                             // box {32 k, goff rows}: h rows, g rows
               tma_load_2d(sb, mb, &full[s], k0, c.n0);
@@ -231,23 +269,32 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           }
         }
       }
+      if (tr) tr[1] = (unsigned long long)w_prod;      // cycles the producer waited for a free stage
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc_full = umma_idesc(TBM, BN, false, B_MN);   // A in TMEM is [m lanes][k columns]
+    // ---------------------------------------------------------------- MMA issuer (pair: the leader CTA only)
+    if (rank == 0 && elect_one_sync()) {
+      constexpr int UM = PAIR ? 2 * TBM : TBM;
+      constexpr uint32_t idesc_full = umma_idesc(UM, BN, false, B_MN);    // A in TMEM is [m lanes][k columns]
       int it = 0, j = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
-        const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
+      long long w_mma = 0, w_acc = 0;
+      for (int t = cta0; t < p.ntiles; t += nct, ++j) {
+        const TileCoord c = tile_coord<BN, EPI, B_MN, CONV, PAIR>(p, t, rank);
         const int acc = j & 1;
-        const uint32_t idesc = c.last ? umma_idesc(TBM, c.neff, false, B_MN) : idesc_full;
-        mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        const uint32_t idesc = c.last ? umma_idesc(UM, c.neff, false, B_MN) : idesc_full;
+        timed_wait(tr != nullptr, w_acc, [&] {
+          if (PAIR) mbar_wait_cluster(&acc_empty[acc], ((j >> 1) & 1) ^ 1);
+          else mbar_wait(&acc_empty[acc], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        });
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         const uint32_t d_cross = DUAL ? d_tmem + BN : d_tmem;
         for (int kb = 0; kb < c.nkb; ++kb, ++it) {
           const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
-          mbar_wait(&conv[s], ph);
+          timed_wait(tr != nullptr, w_mma, [&] {
+            if (PAIR) mbar_wait_cluster(&conv[s], ph);
+            else mbar_wait(&conv[s], ph);
+          });
           tc_fence_after();
           const uint32_t sb_hi = smem_u32(smem + s * STAGE_BYTES) + B_OFF;
           const uint32_t sb_lo = sb_hi + B_BYTES;
@@ -261,16 +308,27 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             const uint64_t b_hi = umma_desc(sb_hi + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint64_t b_lo = umma_desc(sb_lo + boff, B_MN ? 4096 : 16, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
-            umma_tf32_ts(d_cross, ta_hi + 32 + 8 * ks, b_hi, idesc, first);          // A_lo x B_hi: small terms first
-            umma_tf32_ts(d_cross, ta_hi + 8 * ks, b_lo, idesc, 1u);                  // A_hi x B_lo
-            umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, DUAL ? first : 1u);    // A_hi x B_hi
+            if (PAIR) {
+              umma_tf32_ts2(d_tmem, ta_hi + 32 + 8 * ks, b_hi, idesc, first);
+              umma_tf32_ts2(d_tmem, ta_hi + 8 * ks, b_lo, idesc, 1u);
+              umma_tf32_ts2(d_tmem, ta_hi + 8 * ks, b_hi, idesc, 1u);
+            } else {
+              umma_tf32_ts(d_cross, ta_hi + 32 + 8 * ks, b_hi, idesc, first);          // A_lo x B_hi: small terms first
+              umma_tf32_ts(d_cross, ta_hi + 8 * ks, b_lo, idesc, 1u);                  // A_hi x B_lo
+              umma_tf32_ts(d_tmem, ta_hi + 8 * ks, b_hi, idesc, DUAL ? first : 1u);    // A_hi x B_hi
+            }
           }
-          umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+          if (PAIR) umma_commit2(&empty[s]);      // frees the stage in BOTH CTAs once these MMAs have read it
+          else umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
-        if (c.nkb > 0) umma_commit(&acc_full[acc]);   // accumulator complete
-        else mbar_arrive(&acc_full[acc]);
+        if (PAIR) {
+          umma_commit2(&acc_full[acc]);             // (pair GEMMs always have k-blocks)
+        } else {
+          if (c.nkb > 0) umma_commit(&acc_full[acc]);   // accumulator complete
+          else mbar_arrive(&acc_full[acc]);
+        }
       }
-      if (tr) tr[2] = j;
+      if (tr) { tr[2] = j; tr[3] = (unsigned long long)w_mma; tr[4] = (unsigned long long)w_acc; }
     }
   } else if (warp < EPI_WARP0) {
     // ---------------------------------------------------------------- converters (warps 2..9)
@@ -282,11 +340,12 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     const int qd = warp & 3, kh = (warp - 2) >> 2;         // TMEM lane quadrant, half of the k-block
     const int am = 32 * qd + lane;                         // tile row (= TMEM lane) of this thread
     int it = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
+    long long w_conv = 0;
+    for (int t = cta0; t < p.ntiles; t += nct) {
+      const TileCoord c = tile_coord<BN, EPI, B_MN, CONV, PAIR>(p, t, rank);
       for (int kb = 0; kb < c.nkb; ++kb, ++it) {
         const int s = it % TSTAGES, ph = (it / TSTAGES) & 1;
-        mbar_wait(&full[s], ph);
+        timed_wait(tr != nullptr, w_conv, [&] { mbar_wait(&full[s], ph); });
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + B_OFF;
         const int bchunks = c.bbytes >> 4;                   // 16-byte chunks of the B tile that hold data
@@ -325,9 +384,13 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                 make_float4(split_lo(vb[i].x), split_lo(vb[i].y), split_lo(vb[i].z), split_lo(vb[i].w));
         fence_proxy_async();        // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(&conv[s]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&conv[s], 0);      // on the leader's barrier
+          else mbar_arrive(&conv[s]);
+        }
       }
     }
+    if (tr && tid == 64) tr[5] = (unsigned long long)w_conv;   // cycles a converter warp waited for TMA data
   } else {
     // ---------------------------------------------------------------- epilogue (warps 10..13)
     // TMEM gives every thread one output ROW (32 consecutive columns per tcgen05.ld); storing that directly costs
@@ -365,8 +428,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       }
       __syncwarp();
     };
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++j) {
-      const TileCoord c = tile_coord<BN, EPI, B_MN, CONV>(p, t);
+    for (int t = cta0; t < p.ntiles; t += nct, ++j) {
+      const TileCoord c = tile_coord<BN, EPI, B_MN, CONV, PAIR>(p, t, rank);
       const int acc = j & 1;
       mbar_wait(&acc_full[acc], (j >> 1) & 1);
       tc_fence_after();
@@ -526,11 +589,15 @@ __global__ void __launch_bounds__(TTHREADS, 1)
       // all tcgen05.ld of this accumulator have completed (wait::ld): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&acc_empty[acc], 0);
+        else mbar_arrive(&acc_empty[acc]);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (tr && tid == 0) {
     unsigned int sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
@@ -539,7 +606,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
   }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TM_COLS);
+    else tmem_dealloc(tmem_base, TM_COLS);
   }
 }
 
@@ -550,12 +618,12 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
     reinterpret_cast<float4*>(out)[i] = i < n4 ? reinterpret_cast<const float4*>(w0)[i] : reinterpret_cast<const float4*>(w1)[i - n4];
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CONV = 0>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CONV = 0, bool PAIR = false>
 int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, TcParams& p,
            cudaStream_t st) {
-  constexpr int STAGE = TBM * TBK * 4 + 2 * BN * TBK * 4;
+  constexpr int STAGE = TBM * TBK * 4 + 2 * (PAIR ? BN / 2 : BN) * TBK * 4;
   constexpr int SMEM = TSTAGES * STAGE + 1024 + 256 + EP_BYTES;
-  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI, CONV>;
+  auto kern = gemm_tf32x3_kernel<BN, A_MN, B_MN, EPI, CONV, PAIR>;
   static bool configured = false;
   if (!configured) {
     EXVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -564,7 +632,23 @@ int launch(const TcGemm& g, const CUtensorMap& ma, const CUtensorMap& mb, const 
   p.ntn = EPI == TC_GATED ? ceil_div(g.gated_O, BN / 2) : ceil_div(g.N, BN);
   p.ntm = ceil_div(g.M, TBM);
   if (CONV) p.ntm = g.conv->bn == 1 ? g.conv->N * (g.conv->OH / g.conv->bh) : ceil_div(g.conv->N, g.conv->bn);
+  if (PAIR) p.ntm = ceil_div(p.ntm, 2);                  // 256-row tiles: two 128-row units per CTA pair
   p.ntiles = p.ntn * p.ntm * (EPI == TC_SPLITK ? g.splits : 1);
+  if (PAIR) {
+    const int pairs = std::min(p.ntiles, sm_count() / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TTHREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mbl, p);
+    return e == cudaSuccess ? EXVAE_OK : (int)e;
+  }
   const int grid = std::min(p.ntiles, sm_count());     // persistent: one CTA per SM
   kern<<<grid, TTHREADS, SMEM, st>>>(ma, mb, mbl, p);
   cudaError_t e = cudaGetLastError();
@@ -659,6 +743,29 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
   if constexpr (BN == 64) {      // the dual-accumulator prior epilogues only exist for 64-wide tiles (TMEM budget)
     if (g.epi == TC_LSE && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_LSE>(g, ma, mb, mbl, p, st);
     if (g.epi == TC_PW && !g.a_mn && !g.b_mn) return launch<BN, false, false, TC_PW>(g, ma, mb, mbl, p, st);
+  }
+  if constexpr (BN == 128) {
+    // CTA pairs (cta_group::2) for the big K-major forward GEMMs: enough 256-row tiles to fill every pair of SMs
+    if (pair_enabled() && !g.a_mn && !g.b_mn && (g.epi == TC_GATED || g.epi == TC_BIAS_ACT) && g.K >= 64) {
+      const int ntn = g.epi == TC_GATED ? ceil_div(g.gated_O, BN / 2) : ceil_div(g.N, BN);
+      const int units = g.conv ? (g.conv->bn == 1 ? g.conv->N * (g.conv->OH / g.conv->bh) : ceil_div(g.conv->N, g.conv->bn))
+                               : ceil_div(g.M, TBM);
+      if ((long long)ntn * ceil_div(units, 2) >= sm_count() / 2) {
+        CUtensorMap mbp = mb, mblp = mbl;
+        if (g.epi == TC_BIAS_ACT) {          // N/2 rows of the B tile per CTA
+          rc = make_map2d(&mbp, g.b, g.b_rows, g.b_cols, BN / 2, false);
+          if (rc) return rc;
+          rc = make_map2d(&mblp, g.b, g.b_rows, g.b_cols, p.neff_last / 2, false);
+          if (rc) return rc;
+        }
+        if (g.conv) {
+          if (g.epi == TC_GATED) return launch<BN, false, false, TC_GATED, 1, true>(g, ma, mbp, mblp, p, st);
+          return launch<BN, false, false, TC_BIAS_ACT, 1, true>(g, ma, mbp, mblp, p, st);
+        }
+        if (g.epi == TC_GATED) return launch<BN, false, false, TC_GATED, 0, true>(g, ma, mbp, mblp, p, st);
+        return launch<BN, false, false, TC_BIAS_ACT, 0, true>(g, ma, mbp, mblp, p, st);
+      }
+    }
   }
   if (g.conv) {      // implicit-GEMM convolution: forward (gated / bias+activation) and the stride-1 input gradient (plain)
     if (g.a_mn || g.b_mn) return EXVAE_ERR_UNSUPPORTED;

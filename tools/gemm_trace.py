@@ -32,6 +32,11 @@ def summarize(name, buf, launch):
     print(f"{name}: {len(t)} persistent CTAs, kernel span {span:.1f} us; per CTA (median / max):")
     print(f"   tiles per CTA                      {np.median(t[:, 2]):8.0f} {t[:, 2].max():8.0f}")
     print(f"   CTA lifetime (us)                  {np.median(life):8.2f} {life.max():8.2f}")
+    ghz = 1.965e3          # cycles per us (SM clock under load on the B200 boxes)
+    for col, what in ((1, "producer waiting for a free stage"), (5, "converter warp waiting for TMA data"),
+                      (3, "MMA thread waiting for converted operands"), (4, "MMA thread waiting for a drained accumulator")):
+        v = t[:, col] / ghz
+        print(f"   {what:44s} {np.median(v):8.2f} {v.max():8.2f}  us")
 
 
 def timed(fn, n=20):
