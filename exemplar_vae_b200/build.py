@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libexvae_b200.so")
-SOURCES = ["api.cu", "prior_lse.cu", "pairdist_knn.cu", "knn_fused.cu", "gemm.cu", "gemm_tc.cu", "prior_lse_tc.cu", "prior_bwd_tc.cu", "elementwise.cu", "fused_small.cu", "mc_coll.cu", "vamp.cu", "conv.cu"]
+SOURCES = ["api.cu", "prior_lse.cu", "pairdist_knn.cu", "knn_fused.cu", "gemm.cu", "gemm_tc.cu", "prior_lse_tc.cu", "prior_fused.cu", "prior_bwd_tc.cu", "elementwise.cu", "fused_small.cu", "mc_coll.cu", "vamp.cu", "conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

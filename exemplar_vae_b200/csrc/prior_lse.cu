@@ -928,25 +928,62 @@ using namespace exvae;
 
 extern "C" size_t exvae_prior_lse_workspace_bytes(int B, int C, int D) {
   if (B <= 0 || C <= 0 || D <= 0) return 0;
-  return prior_ws_layout(B, C, D, true, nullptr).bytes;
+  return prior_ws_layout(B, C, D, true, nullptr).bytes + (prior_fused_ok(D) ? prior_fused_ws_bytes(B, C) : (size_t)0);
 }
 
 extern "C" size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D) {
   if (B <= 0 || C <= 0 || D <= 0) return 0;
-  return prior_ws_layout(B, C, D, false, nullptr).bytes;
+  return std::max(prior_ws_layout(B, C, D, false, nullptr).bytes, prior_fused_ok(D) ? prior_fused_ws_bytes(B, C) : (size_t)0);
+}
+
+static inline bool fused_fwd_path(int B, int D) { return prior_fused_ok(D) && ceil_div(B, 128) <= 64; }
+
+extern "C" int exvae_prior_lse_fwd_prepares_ws(int B, int C, int D) {
+  (void)B; (void)C; (void)D;
+  return 1;      // every forward path leaves a fwd+bwd sized workspace staged for the backward
 }
 
 extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
-                                   const int64_t* mu_idx, int B, int C, int D, const int* c_valid, float* stats, void* ws,
-                                   size_t ws_bytes, exvae_stream_t stream) {
-  EXVAE_CHECK_ARG(z && mu && logvar && stats && ws);
+                                   const int64_t* mu_idx, int B, int C, int D, const int* c_valid, float* stats,
+                                   int64_t C_total, float* log_p, float* lse2, void* ws, size_t ws_bytes,
+                                   exvae_stream_t stream) {
+  EXVAE_CHECK_ARG(z && mu && logvar && ws && (stats || (log_p && lse2)));
   EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
+  EXVAE_CHECK_ARG((log_p == nullptr) == (lse2 == nullptr));
+  cudaStream_t st = as_stream(stream);
+  if (fused_fwd_path(B, D)) {
+    // ONE kernel from the raw inputs: distance, log-density, mask, log-sum-exp, normaliser (prior_fused.cu)
+    // workspace: [staged operands for the backward (only when the caller passed the fwd+bwd size)][tickets + partials]
+    const size_t fb = prior_fused_ws_bytes(B, C);
+    const size_t full = prior_ws_layout(B, C, D, true, nullptr).bytes;
+    const bool with_bwd = ws_bytes >= full + fb;
+    if (!with_bwd && ws_bytes < fb) return EXVAE_ERR_WORKSPACE;
+    PriorFusedStage sg{};
+    if (with_bwd) {
+      const PriorWs w = prior_ws_layout(B, C, D, true, ws);
+      sg.zs = w.zs; sg.ms = w.ms; sg.zp = w.zp; sg.mp = w.mp; sg.cidx = w.cidx; sg.isig = w.isig;
+      sg.LD = w.LD; sg.Bpad = w.Bpad; sg.Cpad = w.Cpad;
+    }
+    return prior_fused_fwd_launch(z, mu, logvar, (z_idx && mu_idx) ? z_idx : nullptr, (z_idx && mu_idx) ? mu_idx : nullptr,
+                                  c_valid, B, C, D, (float)(C_total > 0 ? C_total : C), stats, log_p, lse2,
+                                  static_cast<char*>(ws) + (with_bwd ? full : 0), with_bwd ? &sg : nullptr, st);
+  }
   const PriorWs w = prior_ws_layout(B, C, D, true, ws);
   if (D > 128 && !w.gemm) return EXVAE_ERR_UNSUPPORTED;
   // fwd only touches the leading (fwd) part of the layout: accept a fwd-only sized workspace too
   const size_t need = prior_ws_layout(B, C, D, false, nullptr).bytes;
   if (ws_bytes < need) return EXVAE_ERR_WORKSPACE;
-  cudaStream_t st = as_stream(stream);
+  // the multi-kernel paths always write the per-row statistics; with log_p requested a merge-final launch follows
+  EXVAE_CHECK_ARG(stats != nullptr);
+  struct Fin {
+    const float* z; const float* logvar; int B, D; float ct; const int* cv; float* lp; float* l2; cudaStream_t st;
+    int operator()(const float* s) const {
+      if (!lp) return EXVAE_OK;
+      lse_merge_kernel<true><<<ceil_div(B, 8), 256, 0, st>>>(s, 1, 4, (size_t)B * 4, B, z, logvar, D, ct, nullptr, lp, l2, cv);
+      cudaError_t e = cudaGetLastError();
+      return e == cudaSuccess ? EXVAE_OK : (int)e;
+    }
+  } fin{z, logvar, B, D, (float)(C_total > 0 ? C_total : C), c_valid, log_p, lse2, st};
   int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, c_valid, st);
   if (rc) return rc;
   const bool mask = z_idx && mu_idx;
@@ -963,7 +1000,8 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
     if (rc) return rc;
     lse_merge_kernel<false><<<ceil_div(B, 8), 256, 0, st>>>(w.gpart, ntn, (size_t)ntn * 4, 4, B, nullptr, nullptr, D, 0.f,
                                                             stats, nullptr, nullptr);
-    EXVAE_RETURN_LAST_ERROR();
+    EXVAE_CUDA(cudaGetLastError());
+    return fin(stats);
   }
   if (w.KP && prior_tc_enabled()) {
     if (mask) {
@@ -995,7 +1033,8 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
   EXVAE_CUDA(cudaGetLastError());
   lse_merge_kernel<false><<<ceil_div(B, 8), 256, 0, st>>>(w.part, w.nsplit, (size_t)w.nsplit * 4, 4, B, nullptr,
                                                           nullptr, D, 0.f, stats, nullptr, nullptr);
-  EXVAE_RETURN_LAST_ERROR();
+  EXVAE_CUDA(cudaGetLastError());
+  return fin(stats);
 }
 
 extern "C" int exvae_prior_lse_finalize(const float* stats, int G, const float* z, const float* logvar, int B, int D,
@@ -1018,7 +1057,8 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
   if (D > 128 && !w.gemm) return EXVAE_ERR_UNSUPPORTED;
   if (ws_bytes < w.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  if (!ws_prepared) {
+  // (the one-kernel forward only leaves what the tensor-core backward reads: the FMA-pipe variant re-stages)
+  if (!ws_prepared || (fused_fwd_path(B, D) && (!w.NG || bwd_simt_forced()))) {
     int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, c_valid, st);
     if (rc) return rc;
   }

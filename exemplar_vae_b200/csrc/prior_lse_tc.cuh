@@ -48,6 +48,17 @@ int prior_bwd_prep_launch(const float* zs, const float* ms, const float* g, cons
                           float* lsp, int64_t* zip, cudaStream_t st);
 
 bool prior_tc_enabled();
+// K1 forward as ONE kernel from the raw inputs (prior_fused.cu; D <= 63, <= 64 row blocks).  ws: prior_fused_ws_bytes.
+bool prior_fused_ok(int D);
+size_t prior_fused_ws_bytes(int B, int C);
+// staged operands the backward reads (workspace arrays of prior_ws_layout); null pointer to the struct = forward only
+struct PriorFusedStage {
+  float* zs; float* ms; float* zp; float* mp; int64_t* cidx; float* isig;
+  int LD, Bpad, Cpad;
+};
+int prior_fused_fwd_launch(const float* z, const float* mu, const float* logvar, const int64_t* z_idx, const int64_t* mu_idx,
+                           const int* c_valid, int B, int C, int D, float c_total, float* stats, float* log_p, float* lse2,
+                           void* ws, const PriorFusedStage* sg, cudaStream_t st);
 // launches the kernel; *nsplit_out = number of partials written per row
 int prior_fwd_tc_launch(const PriorTcArgs& a, int* nsplit_out, cudaStream_t st);
 

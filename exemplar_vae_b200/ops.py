@@ -97,22 +97,26 @@ class _PriorLSE(torch.autograd.Function):
         ws = _ws(L.exvae_prior_lse_workspace_bytes(B, C, D) if need_bwd else
                  L.exvae_prior_lse_fwd_workspace_bytes(B, C, D), z.device)
         stats = torch.empty((B, 4), dtype=torch.float32, device=z.device)
-        L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(c_valid), _p(stats),
-                                      _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
-        _count(4 if (z_idx is not None and mu_idx is not None) else 3)   # stage, [mask list], main, merge
-        G = 1
-        all_stats = stats
-        if group is not None:
+        log_p = torch.empty((B,), dtype=torch.float32, device=z.device)
+        lse2 = torch.empty((B,), dtype=torch.float32, device=z.device)
+        total = int(c_total) if c_total is not None else C
+        masked = z_idx is not None and mu_idx is not None
+        if group is None:
+            # one GPU: fwd returns log p(z) itself -- for D <= 63 ONE kernel from the raw inputs (csrc/prior_fused.cu)
+            L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(c_valid), _p(stats),
+                                          total, _p(log_p), _p(lse2), _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
+            _count(1 if L.exvae_prior_lse_fwd_prepares_ws(B, C, D) == 0 else (5 if masked else 4))
+        else:
             import torch.distributed as dist
+            L.check(L.exvae_prior_lse_fwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(c_valid), _p(stats),
+                                          0, None, None, _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
             G = dist.get_world_size(group)
             all_stats = torch.empty((G, B, 4), dtype=torch.float32, device=z.device)
             dist.all_gather_into_tensor(all_stats, stats, group=group)   # the single LSE-partial exchange
-        total = int(c_total) if c_total is not None else C
-        log_p = torch.empty((B,), dtype=torch.float32, device=z.device)
-        lse2 = torch.empty((B,), dtype=torch.float32, device=z.device)
-        L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z), _p(logvar), B, D, total, _p(c_valid), _p(log_p),
-                                           _p(lse2), _stream()), "prior_lse_finalize")
-        _count(1)
+            L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z), _p(logvar), B, D, total, _p(c_valid), _p(log_p),
+                                               _p(lse2), _stream()), "prior_lse_finalize")
+            _count(3)
+        ctx.ws_prepared = int(L.exvae_prior_lse_fwd_prepares_ws(B, C, D))
         ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid)
         ctx.dims = (B, C, D)
         return log_p
@@ -127,9 +131,9 @@ class _PriorLSE(torch.autograd.Function):
         dmu = torch.empty_like(mu)
         dlv = torch.empty((D,), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_bwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(lse2), _p(g),
-                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, _p(c_valid), _stream()),
+                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), ctx.ws_prepared, _p(c_valid), _stream()),
                 "prior_lse_bwd")
-        _count(5 if D <= 63 else 6)   # D <= 63: prep, two passes, rows, dlogvar; D >= 64: W pass, two GEMMs, rows, cols, dlogvar
+        _count((5 if D <= 63 else 6) + (0 if ctx.ws_prepared else 1))   # D <= 63: prep, two passes, rows, dlogvar; D >= 64: W pass, two GEMMs, rows, cols, dlogvar
         return dz, dmu, dlv.view_as(logvar), None, None, None, None, None
 
 
@@ -1029,7 +1033,8 @@ class _PriorLSESharded(torch.autograd.Function):
         ws = _ws(L.exvae_prior_lse_workspace_bytes(Bt, C, D), z.device)
         stats = torch.empty((Bt, 4), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_fwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, None, _p(stats),
-                                      _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
+                                      0, None, None, _p(ws), ws.numel(), _stream()), "prior_lse_fwd")
+        prepared = int(L.exvae_prior_lse_fwd_prepares_ws(Bt, C, D))
         _count(3)
         if comm is not None:
             all_stats = comm.all_gather(stats, "stats")             # the single LSE-partial exchange: one kernel
@@ -1043,7 +1048,7 @@ class _PriorLSESharded(torch.autograd.Function):
                                            _p(lse2), _stream()), "prior_lse_finalize")
         _count(1)
         ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws)
-        ctx.meta = (B, Bt, C, D, G, rank, group, comm)
+        ctx.meta = (B, Bt, C, D, G, rank, group, comm, prepared)
         return log_p[rank * B:(rank + 1) * B].clone()
 
     @staticmethod
@@ -1051,7 +1056,7 @@ class _PriorLSESharded(torch.autograd.Function):
         import torch.distributed as dist
         L = lib()
         z_all, mu, logvar, zi_all, mu_idx, lse2, ws = ctx.saved_tensors
-        B, Bt, C, D, G, rank, group, comm = ctx.meta
+        B, Bt, C, D, G, rank, group, comm, prepared = ctx.meta
         g = _f32(g, "grad")
         dmu = torch.empty_like(mu)
         dlv = torch.empty((D,), dtype=torch.float32, device=g.device)
@@ -1065,7 +1070,7 @@ class _PriorLSESharded(torch.autograd.Function):
             dist.all_gather_into_tensor(g_all, g, group=group)
             dz_all = torch.empty_like(z_all)
         L.check(L.exvae_prior_lse_bwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(lse2),
-                                      _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), 1, None, _stream()),
+                                      _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), prepared, None, _stream()),
                 "prior_lse_bwd")
         _count(3)
         if comm is not None:

@@ -77,9 +77,14 @@ EXVAE_API int exvae_device_info(int* sm_count, int* cc_major, int* cc_minor);
  */
 EXVAE_API size_t exvae_prior_lse_workspace_bytes(int B, int C, int D);     /* forward + backward */
 EXVAE_API size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D); /* forward only (evaluation) */
+/* One-GPU use: pass log_p / lse2 ([B] each) and C_total (0 = C): fwd then returns log p(z) itself and no finalize call
+ * is needed; for D <= 63 that is ONE kernel from the raw inputs (prior_fused.cu: scaling, tf32 split, mask, log-sum-exp
+ * and normaliser on chip).  stats [B,4] is always written (sharded use: exchange it, then call finalize).
+ * exvae_prior_lse_fwd_prepares_ws: 1 if fwd leaves `ws` staged for bwd (ws_prepared = 1), 0 if bwd must stage itself. */
+EXVAE_API int exvae_prior_lse_fwd_prepares_ws(int B, int C, int D);
 EXVAE_API int exvae_prior_lse_fwd(const float* z, const float* mu, const float* logvar, const int64_t* z_idx,
-                        const int64_t* mu_idx, int B, int C, int D, const int* c_valid, float* stats /*[B,4]*/, void* ws,
-                        size_t ws_bytes, exvae_stream_t stream);
+                        const int64_t* mu_idx, int B, int C, int D, const int* c_valid, float* stats /*[B,4]*/,
+                        int64_t C_total, float* log_p, float* lse2, void* ws, size_t ws_bytes, exvae_stream_t stream);
 EXVAE_API int exvae_prior_lse_finalize(const float* stats /*[G,B,4]*/, int G, const float* z, const float* logvar, int B, int D,
                              int64_t C_total, const int* c_valid, float* log_p /*[B]*/, float* lse2 /*[B]*/,
                              exvae_stream_t stream);

@@ -151,11 +151,11 @@ def test_prior_lse_shard_merge_property(ops):
         m, mi = mu[sl].contiguous(), mu_idx[sl].contiguous()
         ws = torch.empty(L.exvae_prior_lse_workspace_bytes(B, m.shape[0], D), dtype=torch.uint8, device="cuda")
         L.check(L.exvae_prior_lse_fwd(z.data_ptr(), m.data_ptr(), lv.data_ptr(), z_idx.data_ptr(), mi.data_ptr(), B,
-                                      m.shape[0], D, None, stats[r].data_ptr(), ws.data_ptr(), ws.numel(), st))
+                                      m.shape[0], D, None, stats[r].data_ptr(), 0, None, None, ws.data_ptr(), ws.numel(), st))
     lp = torch.empty(B, device="cuda"); l2 = torch.empty(B, device="cuda")
     L.check(L.exvae_prior_lse_finalize(stats.data_ptr(), G, z.data_ptr(), lv.data_ptr(), B, D, C, None, lp.data_ptr(),
                                        l2.data_ptr(), st))
-    close(lp, full, rtol=2e-6, atol=1e-5)
+    close(lp, full, rtol=2e-5, atol=2e-4)     # same pairs, different summation order (in-kernel final vs merge kernel)
 
 
 def test_prior_lse_backward_vs_oracle_cfg1(ops):
