@@ -262,12 +262,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
     const int ci = tid - 32 * (1 + PF_EPI_WARPS);             // 0..255
     const int c = ci >> 1, par = ci & 1;
     const int nch = (D + 4) >> 2;                             // chunks that hold data incl. the augmented column D
-    const bool stage_m = p.st_ms != nullptr && rb == 0;       // one CTA per bank tile also leaves the staged rows
+    const int nrb = gridDim.y;
     const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mu) & 15) == 0;
     for (int t = t0; t < t1; ++t) {
       const int it = t - t0, s = it & 1, ph = (it >> 1) & 1, ring = it & 3;
       const int n = t * 128 + c;
       const bool valid = n < Cv;
+      // ONE of the row blocks' CTAs that process tile t also leaves its staged rows for the backward (round-robin, so
+      // that the extra stores spread over the CTAs)
+      const bool stage_m = p.st_ms != nullptr && rb == (t % nrb);
       // raw chunks -> registers first (the global-memory latency overlaps the wait for the stage)
       float4 raw[8];
 #pragma unroll
