@@ -274,19 +274,34 @@ class BaseModel(nn.Module, ABC):
             emb = ShardedBank(emb, c_total)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
+            ops.take_prior_fwd_event()
             log_p_z = self.log_p_z(z=(z_q, x_indices), exemplars_embedding=emb)
-        self._log_p_z_early = (log_p_z, side)
+            # with a known upstream gradient the branch goes on into the K1 backward: the loss waits for the forward only
+            ev = ops.take_prior_fwd_event()
+        self._log_p_z_early = (log_p_z, side, ev)
 
     def _log_p_z_branch(self, z_q, x_indices, exemplars_embedding):
         """log p(z) of the exemplar prior: the result of the side-stream branch forked in forward(), else computed here."""
         early, self._log_p_z_early = self._log_p_z_early, None
         if early is not None:
-            log_p_z, side = early
+            log_p_z, side, ev = early
             cur = torch.cuda.current_stream()
-            cur.wait_stream(side)
+            if ev is not None:
+                cur.wait_event(ev)
+            else:
+                cur.wait_stream(side)
             log_p_z.record_stream(cur)
             return log_p_z
         return self.log_p_z(z=(z_q, x_indices), exemplars_embedding=exemplars_embedding)
+
+    def _known_prior_grad(self, rows):
+        """d loss / d log p(z_b) for every row, when the caller of calculate_loss has announced it (``prior_grad_known``,
+        set by GraphedTrainStep around its own loss = mean(-RE + beta*KL)): the K1 backward then runs right behind the K1
+        forward, next to the decoder.  None (the default) keeps the ordinary autograd backward."""
+        g = getattr(self, "prior_grad_known", None)
+        if g is None or not self.training or not torch.is_grad_enabled() or g.numel() != rows:
+            return None
+        return g
 
     def _prior_stream(self):
         dev = torch.cuda.current_device()
@@ -339,9 +354,11 @@ class BaseModel(nn.Module, ABC):
             c_total = getattr(exemplars_embedding, "c_total", None)
             if c_total is not None and self.bank_group is not None:     # range-sharded bank (distributed.py)
                 return ops.prior_lse_sharded(z, centers, lv, z_indices if masked else None,
-                                             center_indices if masked else None, c_total, self.bank_group)
+                                             center_indices if masked else None, c_total, self.bank_group,
+                                             g_known=self._known_prior_grad(z.shape[0] * self.bank_world))
             return ops.prior_lse(z, centers, lv, z_indices if masked else None, center_indices if masked else None,
-                                 c_valid=getattr(exemplars_embedding, "valid_count", None))
+                                 c_valid=getattr(exemplars_embedding, "valid_count", None),
+                                 g_known=self._known_prior_grad(z.shape[0]))
         raise Exception('Wrong name of the prior!')
 
     # ------------------------------------------------------------------ generation helpers

@@ -593,14 +593,21 @@ inline void tc_stage_geometry(TcBwdPlan& b, int R, int O) {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  bool pending = false;      // a deferred dW finish has been queued and not yet joined (exvae_dense_bwd_flush)
 };
+// exvae_dense_bwd_defer_finish: the dW finish of the LARGE layers is forked and NOT joined by the backward call
+bool g_defer_finish = false;
 inline SideStream* side_stream() {
   static SideStream table[16];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
   SideStream& s = table[dev];
   if (!s.stream) {
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: the forked dW GEMMs belong to the main chain of the step (the exemplar-prior branch runs its
+    // whole-GPU kernels on a default = low priority stream next to them)
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { (void)cudaGetLastError(); prio_hi = 0; }
+    if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
       (void)cudaGetLastError();
@@ -652,7 +659,17 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K,
     g.splits = plan.S; g.kchunk = plan.kchunk;
     rc = tc_gemm_launch(g, sw);
     if (rc) return rc;
-    // split-K reduction of dW and the bias gradients (column sums of the staging blocks) in one launch
+    // split-K reduction of dW and the bias gradients (column sums of the staging blocks) in one launch.
+    // Large layers with a deferred finish: this launch-bound pass (5-14 us) goes to the side stream and is joined by
+    // exvae_dense_bwd_flush (or by the next fork/join on that stream), so that it runs next to the following layer's
+    // staging kernel instead of in front of it.  The caller keeps `ws` alive until the flush.
+    SideStream* dside = (!side && g_defer_finish && accumulate) ? side_stream() : nullptr;
+    if (dside) {
+      EXVAE_CUDA(cudaEventRecord(dside->fork, st));
+      EXVAE_CUDA(cudaStreamWaitEvent(dside->stream, dside->fork, 0));
+      sw = dside->stream;
+      dside->pending = true;
+    }
     const int nred = ew_blocks((long long)ncat * K);
     const int ncs = (db0 || db1) ? ceil_div(ncat, 32) : 0;
     dw_finish_kernel<<<nred + ncs, 256, 0, sw>>>(part, plan.S, ncat, K, oseg, dW0, dW1 ? dW1 : dW0, nred,
@@ -663,6 +680,7 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K,
   if (side) {
     EXVAE_CUDA(cudaEventRecord(side->join, side->stream));
     EXVAE_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    side->pending = false;       // the side stream is in order: this join also covers an earlier deferred finish
   }
   return EXVAE_OK;
 }
@@ -684,9 +702,15 @@ extern "C" int exvae_gated_dense_fwd(const float* x, const float* Wh, const floa
   cudaStream_t st = as_stream(stream);
   const FwdWs f = fwd_ws_layout(R, K, 2 * O, true);
   if (ws && ws_bytes >= f.bytes && tc_ok(R, K, 2 * O, x) && al16(Wh) && al16(Wg) && al16(ws)) {
-    float* wsp = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_w);
-    int rc = tc_concat2(Wh, Wg, (size_t)O * K, wsp, st);
-    if (rc) return rc;
+    // [Wh ; Wg] as ONE operand: when the caller keeps the two weights adjacent in memory (layers.GatedDense packs them
+    // into one [2*O, K] buffer) Wh already IS that operand and the copy disappears
+    const float* wsp = Wh;
+    if (Wg != Wh + (size_t)O * K) {
+      float* wown = reinterpret_cast<float*>(static_cast<char*>(ws) + f.off_w);
+      int rc = tc_concat2(Wh, Wg, (size_t)O * K, wown, st);
+      if (rc) return rc;
+      wsp = wown;
+    }
     TcGemm g{};
     g.a = x; g.a_rows = R; g.a_cols = K; g.a_mn = false;
     g.b = wsp; g.b_rows = 2 * O; g.b_cols = K; g.b_mn = false;
@@ -729,7 +753,8 @@ extern "C" int exvae_gated_dense_bwd(const float* x, const float* Wh, const floa
     EXVAE_CUDA(cudaGetLastError());
     const FwdWs f = fwd_ws_layout(R, K, 2 * O, true);
     const bool reuse = fwd_ws && fwd_ws_bytes >= f.bytes && al16(fwd_ws);
-    const float* wsp = reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
+    const float* wsp = (Wg == Wh + (size_t)O * K) ? Wh          // adjacent weights: no [Wh ; Wg] copy exists or is needed
+                       : reuse ? reinterpret_cast<const float*>(static_cast<const char*>(fwd_ws) + f.off_w) : nullptr;
     return dense_bwd_tc(x, Wh, Wg, R, K, 2 * O, O, dx, dWh, dWg, dbh, dbg, wsp, plan, w, accumulate, st);
   }
   const BwdPlan plan = bwd_plan(R, K, 2 * O, true);
@@ -803,6 +828,22 @@ extern "C" int exvae_linear_bwd(const float* x, const float* W, const float* out
 }
 
 extern "C" int exvae_gemm_backend(void) { return tc_enabled() ? 1 : 0; }
+extern "C" int exvae_dense_bwd_defer_finish(int on) {
+  const int prev = g_defer_finish ? 1 : 0;
+  g_defer_finish = on != 0;
+  return prev;
+}
+
+extern "C" int exvae_dense_bwd_flush(exvae_stream_t stream) {
+  SideStream* side = side_stream();
+  if (side && side->pending) {
+    EXVAE_CUDA(cudaEventRecord(side->join, side->stream));
+    EXVAE_CUDA(cudaStreamWaitEvent(as_stream(stream), side->join, 0));
+    side->pending = false;
+  }
+  return EXVAE_OK;
+}
+
 extern "C" int exvae_gemm_set_trace(uint64_t* buf) {
   tc_set_trace(reinterpret_cast<unsigned long long*>(buf));
   return EXVAE_OK;

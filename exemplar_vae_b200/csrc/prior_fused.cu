@@ -21,6 +21,7 @@
 
 #include <algorithm>
 
+#include "gemm_tc.cuh"
 #include "tc_common.cuh"
 
 namespace exvae {
@@ -35,10 +36,16 @@ constexpr int PF_HASH = 256;
 constexpr int PF_HITS = 128;                        // columns of one tile that can be masked (<= 128 by construction)
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+// 3xTF32 operand split in 5 integer / fp32 instructions per element (cvt.rna.tf32.f32 is emulated with ~4 instructions
+// each on sm_100a, and the converter warps are latency bound): adding half an ulp of the 10-bit mantissa to the bit
+// pattern and clearing the 13 low bits is round-to-nearest (ties away), i.e. what cvt.rna.tf32.f32 returns for finite
+// values.  hi = rna(x); x - hi is exact; lo = rna(x - hi).  BOTH parts are rounded, not truncated: the logits are
+// differences of terms ~|mu/sigma|^2 (1e3), and a truncated hi makes |lo| twice as large and the dropped lo*lo term
+// four times as large (measured: 5e-4 absolute on log p(z), outside the 5e-5 relative bar of the goldens).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& h, uint32_t& l) {
+  h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  const float r = x - __uint_as_float(h);
+  l = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
 }
 // byte offset of element (row r, k) inside the [nkb][2 planes] operand region: SWIZZLE_128B K-major tiles of 32 floats
 __device__ __forceinline__ uint32_t op_off(int r, int k, int plane) {
@@ -46,10 +53,26 @@ __device__ __forceinline__ uint32_t op_off(int r, int k, int plane) {
   return (uint32_t)((kb * 2 + plane) * PF_TILE + r * 128 + ((((kk >> 2) ^ (r & 7))) << 4) + (kk & 3) * 4);
 }
 __device__ __forceinline__ void put_split(unsigned char* base, int r, int k, float x) {
-  const uint32_t h = tf32_rna(x);
-  const uint32_t l = tf32_rna(x - __uint_as_float(h));
+  uint32_t h, l;
+  split_tf32(x, h, l);
   *reinterpret_cast<uint32_t*>(base + op_off(r, k, 0)) = h;
   *reinterpret_cast<uint32_t*>(base + op_off(r, k, 1)) = l;
+}
+__device__ __forceinline__ unsigned long long pf_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug (trace runs only): cycles spent inside a barrier wait
+template <typename F>
+__device__ __forceinline__ void pf_timed_wait(bool on, long long& acc, F&& wait) {
+  if (on) {
+    const long long t0 = clock64();
+    wait();
+    acc += clock64() - t0;
+  } else {
+    wait();
+  }
 }
 __device__ __forceinline__ uint32_t hash_key(long long k) {
   unsigned long long x = (unsigned long long)k * 0x9E3779B97F4A7C15ull;
@@ -72,9 +95,10 @@ struct PfParams {
   int64_t* st_cidx;            // [Cpad] dataset index per exemplar (INT64_MIN beyond the valid rows)
   float* st_isig;              // [LD]
   int LD, Bpad, Cpad;
+  unsigned long long* trace;   // debug (exvae_gemm_set_trace): 8 words per CTA, null in production
 };
 
-template <bool MASK>
+template <bool MASK, int NJ>
 __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const PfParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -103,8 +127,32 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
   const int D = p.D, KP = p.KP;
   const int nks = KP / 8;
   const int Cv = p.c_valid ? min(p.C, max(*p.c_valid, 0)) : p.C;
+#ifdef EXVAE_PF_TRACE      // per-role wait trace (tools/prior_fwd_trace.py): debug builds only
+  unsigned long long* const tr = p.trace ? p.trace + 8 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+#else
+  constexpr unsigned long long* tr = nullptr;
+#endif
+  if (tr && tid == 0) tr[0] = pf_gtimer();
 
   // ------------------------------------------------------------------ prologue
+  // z rows of this block: issued first, so that their global-memory latency hides behind the barrier / TMEM / zeroing
+  // work below (vector path: D % 4 == 0, i.e. every 16-byte chunk of the swizzled operand row comes from one float4)
+  constexpr int ZI = 4;                                       // 128 rows x <= 15 float4 over 544 threads
+  const int nq = D >> 2;
+  const bool zvec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0;
+  float4 zr[ZI];
+  if (zvec) {
+#pragma unroll
+    for (int i = 0; i < ZI; ++i) {
+      const int e = tid + i * PF_THREADS;
+      zr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < 128 * nq) {
+        const int r = e / nq, q = e - r * nq;
+        const int b = rb * 128 + r;
+        if (b < p.B) zr[i] = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)b * D) + q);
+      }
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&b_full[i], 8);
@@ -126,13 +174,36 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
   const uint32_t tmem_base = *tmem_slot;
   // A operand: z' = (z / sigma * log2e | 1 | 0..), hi/lo tf32 planes
   const bool stage_z = p.st_zs != nullptr && split == 0;      // one CTA per row block also leaves the staged z rows
-  for (int e = tid; e < 128 * D; e += PF_THREADS) {
-    const int r = e / D, k = e - r * D;
-    const int b = rb * 128 + r;
-    if (b < p.B) {
-      const float zsv = p.z[(size_t)b * D + k] * isig[k];
-      put_split(sA, r, k, zsv * kLog2e);
-      if (stage_z) p.st_zs[(size_t)b * p.LD + k] = zsv;
+  if (zvec) {
+#pragma unroll
+    for (int i = 0; i < ZI; ++i) {
+      const int e = tid + i * PF_THREADS;
+      if (e < 128 * nq) {
+        const int r = e / nq, q = e - r * nq;
+        const int b = rb * 128 + r;
+        if (b < p.B) {
+          const float4 is4 = *reinterpret_cast<const float4*>(isig + 4 * q);
+          const float4 zs4 = make_float4(zr[i].x * is4.x, zr[i].y * is4.y, zr[i].z * is4.z, zr[i].w * is4.w);
+          const float v[4] = {zs4.x * kLog2e, zs4.y * kLog2e, zs4.z * kLog2e, zs4.w * kLog2e};
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) split_tf32(v[c4], h[c4], l[c4]);
+          const uint32_t off = (uint32_t)((q >> 3) * 2 * PF_TILE + r * 128 + ((((q & 7) ^ (r & 7))) << 4));
+          *reinterpret_cast<uint4*>(sA + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(sA + off + PF_TILE) = make_uint4(l[0], l[1], l[2], l[3]);
+          if (stage_z) *reinterpret_cast<float4*>(p.st_zs + (size_t)b * p.LD + 4 * q) = zs4;   // LD % 4 == 0
+        }
+      }
+    }
+  } else {
+    for (int e = tid; e < 128 * D; e += PF_THREADS) {
+      const int r = e / D, k = e - r * D;
+      const int b = rb * 128 + r;
+      if (b < p.B) {
+        const float zsv = p.z[(size_t)b * D + k] * isig[k];
+        put_split(sA, r, k, zsv * kLog2e);
+        if (stage_z) p.st_zs[(size_t)b * p.LD + k] = zsv;
+      }
     }
   }
   if (stage_z) {
@@ -172,15 +243,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
     }
   }
 
+  if (tr && tid == 0) tr[1] = pf_gtimer();
   if (warp == 0) {
     // ------------------------------------------------------------- MMA issuer
     if (elect_one_sync()) {
+      long long w_full = 0, w_acc = 0;
       constexpr uint32_t idesc = umma_idesc(128, 128, false, false);
       const uint32_t a0 = smem_u32(sA);
       for (int t = t0; t < t1; ++t) {
         const int it = t - t0, s = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(&b_full[s], ph);
-        mbar_wait(&acc_empty[s], ph ^ 1);
+        pf_timed_wait(tr != nullptr, w_full, [&] { mbar_wait(&b_full[s], ph); });
+        pf_timed_wait(tr != nullptr, w_acc, [&] { mbar_wait(&acc_empty[s], ph ^ 1); });
         tc_fence_after();
         const uint32_t b0 = smem_u32(sB + s * 4 * PF_TILE);
         for (int ks = 0; ks < nks; ++ks) {
@@ -196,6 +269,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
         umma_commit(&b_empty[s]);
         umma_commit(&acc_full[s]);
       }
+      if (tr) { tr[3] = (unsigned long long)w_full; tr[4] = (unsigned long long)w_acc; }
     }
   } else if (warp <= PF_EPI_WARPS) {
     // ------------------------------------------------------------- epilogue warps 1..8
@@ -205,10 +279,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
     const int b = rb * 128 + r;
     const long long zi = (MASK && b < p.B) ? p.z_idx[b] : kPadKey;
     float m = -INFINITY, ssum = 0.f, cnt = 0.f;
+    long long w_epi = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16) + half * 64;
     for (int t = t0; t < t1; ++t) {
       const int it = t - t0, s = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(&acc_full[s], ph);
+      pf_timed_wait(tr != nullptr, w_epi, [&] { mbar_wait(&acc_full[s], ph); });
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld32(lane_addr + s * 128, v0);
@@ -246,6 +321,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
       ssum = acc;
       m = mn;
     }
+    if (tr && tid == 32) tr[5] = (unsigned long long)w_epi;
     if (half == 1) {
       red[r] = make_float2(m, ssum);
       redc[r] = cnt;
@@ -258,29 +334,25 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
     }
   } else {
     // ------------------------------------------------------------- converter warps 9..16: two threads per exemplar
-    // (even / odd 16-byte chunks of its row); 4 consecutive k-values = one swizzled chunk = one 128-bit store per plane
+    // (even / odd 16-byte chunks of its row); 4 consecutive k-values = one swizzled chunk = one 128-bit store per plane.
+    // The raw rows (and dataset indices) of tile t+1 are loaded into registers BEFORE tile t is converted, so that the
+    // global-memory latency hides behind the conversion and the wait for the stage (NJ = chunks per thread).
     const int ci = tid - 32 * (1 + PF_EPI_WARPS);             // 0..255
     const int c = ci >> 1, par = ci & 1;
     const int nch = (D + 4) >> 2;                             // chunks that hold data incl. the augmented column D
     const int nrb = gridDim.y;
     const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mu) & 15) == 0;
-    for (int t = t0; t < t1; ++t) {
-      const int it = t - t0, s = it & 1, ph = (it >> 1) & 1, ring = it & 3;
+    auto load_tile = [&](int t, float4 (&raw)[NJ], long long& key) {
       const int n = t * 128 + c;
       const bool valid = n < Cv;
-      // ONE of the row blocks' CTAs that process tile t also leaves its staged rows for the backward (round-robin, so
-      // that the extra stores spread over the CTAs)
-      const bool stage_m = p.st_ms != nullptr && rb == (t % nrb);
-      // raw chunks -> registers first (the global-memory latency overlaps the wait for the stage)
-      float4 raw[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int ch = 2 * j + par;
         raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid && 4 * ch < D) {
           const float* src = p.mu + (size_t)n * D + 4 * ch;
           if (vec) {
-            raw[j] = *reinterpret_cast<const float4*>(src);
+            raw[j] = __ldg(reinterpret_cast<const float4*>(src));
           } else {
             raw[j].x = src[0];
             if (4 * ch + 1 < D) raw[j].y = src[1];
@@ -289,27 +361,41 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
           }
         }
       }
-      mbar_wait(&b_empty[s], ph ^ 1);
+      key = kPadKey;
+      if (MASK && valid && par == 0) key = p.mu_idx[n];
+    };
+    float4 sc[NJ];
+    long long key;
+    long long w_conv = 0;
+    if (t0 < t1) load_tile(t0, sc, key);
+    for (int t = t0; t < t1; ++t) {
+      const int it = t - t0, s = it & 1, ph = (it >> 1) & 1, ring = it & 3;
+      const int n = t * 128 + c;
+      const bool valid = n < Cv;
+      // ONE of the row blocks' CTAs that process tile t also leaves its staged rows for the backward (round-robin, so
+      // that the extra stores spread over the CTAs)
+      const bool stage_m = p.st_ms != nullptr && rb == (t % nrb);
+      float4 nxt[NJ];
+      long long nkey = kPadKey;
+      if (t + 1 < t1) load_tile(t + 1, nxt, nkey);
+      pf_timed_wait(tr != nullptr, w_conv, [&] { mbar_wait(&b_empty[s], ph ^ 1); });
       unsigned char* sb = sB + s * 4 * PF_TILE;
       if (ci == 0) hits_n[ring] = 0;       // slot free: the epilogue of tile it-4 released it long ago (see ring depth)
-      float ss = 0.f;
-      float4 sc[8];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;           // independent chains: the warps here are latency bound
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int ch = 2 * j + par;
-        const int k0 = 4 * ch;
-        sc[j].x = raw[j].x * isig[min(k0, 63)];
-        sc[j].y = raw[j].y * isig[min(k0 + 1, 63)];
-        sc[j].z = raw[j].z * isig[min(k0 + 2, 63)];
-        sc[j].w = raw[j].w * isig[min(k0 + 3, 63)];
-        ss = fmaf(sc[j].x, sc[j].x, ss); ss = fmaf(sc[j].y, sc[j].y, ss);
-        ss = fmaf(sc[j].z, sc[j].z, ss); ss = fmaf(sc[j].w, sc[j].w, ss);
+        const float4 is4 = *reinterpret_cast<const float4*>(isig + 4 * min(ch, 15));
+        sc[j].x *= is4.x; sc[j].y *= is4.y; sc[j].z *= is4.z; sc[j].w *= is4.w;
+        s0 = fmaf(sc[j].x, sc[j].x, s0); s1 = fmaf(sc[j].y, sc[j].y, s1);
+        s2 = fmaf(sc[j].z, sc[j].z, s2); s3 = fmaf(sc[j].w, sc[j].w, s3);
       }
+      float ss = (s0 + s1) + (s2 + s3);
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);             // the two threads of a row
       const float nb2 = valid ? -0.5f * ss * kLog2e : -1e30f; // finite "minus infinity": an invalid column vanishes
       named_bar(2, 256);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int ch = 2 * j + par;
         if (ch < nch) {
           float v[4] = {sc[j].x, sc[j].y, sc[j].z, sc[j].w};
@@ -318,10 +404,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
             if (4 * ch + e == D) v[e] = nb2;                  // augmented column
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            h[e] = tf32_rna(v[e]);
-            l[e] = tf32_rna(v[e] - __uint_as_float(h[e]));
-          }
+          for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
           const uint32_t off = (uint32_t)((ch >> 3) * 2 * PF_TILE + c * 128 + ((((ch & 7) ^ (c & 7))) << 4));
           *reinterpret_cast<uint4*>(sb + off) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(sb + off + PF_TILE) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -341,10 +424,19 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
               make_float4(4 * ch < D ? sc[j].x : 0.f, 4 * ch + 1 < D ? sc[j].y : 0.f, 4 * ch + 2 < D ? sc[j].z : 0.f,
                           4 * ch + 3 < D ? sc[j].w : 0.f);
       }
-      if (stage_m && par == 0)
-        p.st_cidx[n] = valid ? (p.mu_idx ? p.mu_idx[n] : (int64_t)-1) : (int64_t)kPadKey;
+      if (stage_m) {
+        // chunks beyond the NJ this thread converts (only when KP / LD reach past 8 * NJ floats): zero padding
+        for (int ch = 2 * NJ + par; 4 * ch < max(KP, p.LD); ch += 2) {
+          if (4 * ch < KP) {
+            float* mp = p.st_mp + (size_t)n * KP + 4 * ch;
+            *reinterpret_cast<uint4*>(mp) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(mp + (size_t)p.Cpad * KP) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (4 * ch < p.LD) *reinterpret_cast<float4*>(p.st_ms + (size_t)n * p.LD + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (par == 0) p.st_cidx[n] = valid ? (p.mu_idx ? p.mu_idx[n] : (int64_t)-1) : (int64_t)kPadKey;
+      }
       if (MASK && valid && par == 0) {
-        const long long key = p.mu_idx[n];
         uint32_t slot = hash_key(key);
         while (true) {
           const long long hk = hkeys[slot];
@@ -361,13 +453,18 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_full[s]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) sc[j] = nxt[j];
+      key = nkey;
     }
+    if (tr && ci == 0) tr[2] = (unsigned long long)w_conv;
   }
 
   // ------------------------------------------------------------------ last CTA of the row block: merge + finalize
   tc_fence_before();
   __threadfence();
   __syncthreads();
+  if (tr && tid == 0) tr[6] = pf_gtimer();
   if (tid == 0) {
     const unsigned int prev = atomicAdd(&p.tickets[rb], 1u);
     const int last = prev == (unsigned int)(p.nsplit - 1);
@@ -379,33 +476,78 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prior_fused_fwd_kernel(const Pf
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
-  if (!*s_last) return;
+  if (!*s_last) {
+    if (tr && tid == 0) tr[7] = pf_gtimer();
+    return;
+  }
   __threadfence();
-  if (tid < 128) {
-    const int b = rb * 128 + tid;
-    if (b < p.B) {
-      float m = -INFINITY, s = 0.f, cnt = 0.f;
-      for (int q = 0; q < p.nsplit; ++q) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part) + (size_t)b * p.nsplit + q);
-        lse2_merge(m, s, v.x, v.y);
-        cnt += v.z;
+  // Merge of the row block's per-split partials + normaliser: FOUR threads per row (the partials of a row are contiguous,
+  // so the four read interleaved 16-byte entries), every thread's loads issued in independent batches of 8 -- a single
+  // thread per row walking its 37 partials one L2 round trip at a time cost 16 us at cfg2.
+  float* cst_s = reinterpret_cast<float*>(red);               // [1] (the epilogue's scratch is free now)
+  if (warp == 0) {
+    float c0 = 0.f;
+    for (int d = lane; d < D; d += 32) c0 += p.logvar[d] + kLog2Pi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    if (lane == 0) *cst_s = c0;
+  }
+  __syncthreads();
+  if (tid < 512) {
+    const int r = tid >> 2, sub = tid & 3;
+    const int b = rb * 128 + r;
+    const bool rowok = b < p.B;
+    float m = -INFINITY, s = 0.f, cnt = 0.f;
+    const float4* pp = reinterpret_cast<const float4*>(p.part) + (size_t)b * p.nsplit;     // b < Bpad: in range
+    for (int q0 = sub; q0 < p.nsplit; q0 += 32) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = q0 + 4 * i;
+        v[i] = (rowok && q < p.nsplit) ? __ldcg(pp + q) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        lse2_merge(m, s, v[i].x, v[i].y);
+        cnt += v[i].z;
+      }
+    }
+    // |z_b / sigma|^2: the four threads take every fourth 16-byte chunk (or every fourth element) of the row
+    float hz = 0.f;
+    if (rowok && p.log_p) {
+      if (zvec) {
+        for (int q = sub; q < nq; q += 4) {
+          const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)b * D) + q);
+          const float4 is4 = *reinterpret_cast<const float4*>(isig + 4 * q);
+          const float v0 = zv.x * is4.x, v1 = zv.y * is4.y, v2 = zv.z * is4.z, v3 = zv.w * is4.w;
+          hz = fmaf(v0, v0, hz); hz = fmaf(v1, v1, hz); hz = fmaf(v2, v2, hz); hz = fmaf(v3, v3, hz);
+        }
+      } else {
+        for (int d = sub; d < D; d += 4) {
+          const float v = p.z[(size_t)b * D + d] * isig[d];
+          hz = fmaf(v, v, hz);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {                        // the four threads of a row are neighbouring lanes
+      const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+      lse2_merge(m, s, om, os);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      hz += __shfl_xor_sync(0xffffffffu, hz, o);
+    }
+    if (rowok && sub == 0) {
       if (p.stats) reinterpret_cast<float4*>(p.stats)[b] = make_float4(m, s, cnt, 0.f);
       if (p.log_p) {
-        float hz = 0.f, cst = 0.f;
-        for (int d = 0; d < D; ++d) {
-          const float lv = p.logvar[d];
-          const float v = p.z[(size_t)b * D + d] / expf(0.5f * lv);
-          hz = fmaf(v, v, hz);
-          cst += lv + kLog2Pi;
-        }
         const float l2 = m + log2f(s);
         const float ct = p.c_valid ? (float)*p.c_valid : p.c_total;
         p.lse2[b] = l2;
-        p.log_p[b] = (-0.5f * cst - 0.5f * hz) + kLn2 * l2 - logf(ct - cnt);
+        p.log_p[b] = (-0.5f * *cst_s - 0.5f * hz) + kLn2 * l2 - logf(ct - cnt);
       }
     }
   }
+  __syncthreads();
+  if (tr && tid == 0) tr[7] = pf_gtimer() | (1ull << 63);     // top bit: this CTA did the merge
 }
 
 }  // namespace
@@ -440,6 +582,7 @@ int prior_fused_fwd_launch(const float* z, const float* mu, const float* logvar,
     p.st_zs = sg->zs; p.st_ms = sg->ms; p.st_zp = sg->zp; p.st_mp = sg->mp; p.st_cidx = sg->cidx; p.st_isig = sg->isig;
     p.LD = sg->LD; p.Bpad = sg->Bpad; p.Cpad = sg->Cpad;
   }
+  p.trace = tc_take_trace(8 * 400);
   EXVAE_CUDA(cudaMemsetAsync(p.tickets, 0, 256, st));          // caller-owned workspace may be uninitialised
   constexpr int SMEM = 12 * PF_TILE + 256 + 2048 + 16 + 2048 + 4096 + 1024 + 512 + 128 + 1024;
   dim3 grid(nsplit, rbs);
@@ -450,7 +593,11 @@ int prior_fused_fwd_launch(const float* z, const float* mu, const float* logvar,
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? EXVAE_OK : (int)e;
   };
-  return mask ? launch(prior_fused_fwd_kernel<true>) : launch(prior_fused_fwd_kernel<false>);
+  // NJ = 16-byte chunks of an exemplar row per converter thread (two threads per row): ceil(((D + 4) / 4) / 2)
+  const int nj = (((D + 4) >> 2) + 1) >> 1;
+  if (nj <= 4) return mask ? launch(prior_fused_fwd_kernel<true, 4>) : launch(prior_fused_fwd_kernel<false, 4>);
+  if (nj <= 6) return mask ? launch(prior_fused_fwd_kernel<true, 6>) : launch(prior_fused_fwd_kernel<false, 6>);
+  return mask ? launch(prior_fused_fwd_kernel<true, 8>) : launch(prior_fused_fwd_kernel<false, 8>);
 }
 
 }  // namespace exvae

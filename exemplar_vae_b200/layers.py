@@ -77,6 +77,32 @@ class GatedDense(nn.Module):
             self.activation = torch.nn.ReLU()
         if self.no_attention is False and self.activation is not None:
             raise NotImplementedError("GatedDense with an inner activation is not used by the in-scope models")
+        self._pack()
+
+    def _pack(self):
+        """Keep ``h.weight`` and ``g.weight`` ADJACENT in one [2*O, K] buffer (the two parameters become views of it;
+        names, shapes and ``state_dict`` are unchanged): the fused GEMM reads [Wh ; Wg] as one operand, and with the
+        weights stored that way the per-call concat copy (one launch per layer per step) disappears.  A module whose
+        weights are not adjacent (e.g. after ``copy.deepcopy``) still works: the C side copies then."""
+        if self.no_attention is not False:
+            return
+        h, g = self.h.weight, self.g.weight
+        if h.device != g.device or h.dtype != g.dtype or h.shape != g.shape:
+            return
+        if g.data_ptr() == h.data_ptr() + h.numel() * h.element_size():
+            return
+        O, K = h.shape
+        with torch.no_grad():
+            buf = torch.empty((2 * O, K), dtype=h.dtype, device=h.device)
+            buf[:O].copy_(h.data)
+            buf[O:].copy_(g.data)
+            h.data = buf[:O]
+            g.data = buf[O:]
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)       # .cuda() / .to(): every parameter moves on its own
+        self._pack()
+        return out
 
     def forward(self, x):
         if self.no_attention is False:

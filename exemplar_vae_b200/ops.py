@@ -75,9 +75,26 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 # ======================================================================================
 # K1: fused exemplar prior
 # ======================================================================================
+_prior_fwd_event = None
+
+
+def _mark_prior_fwd_done():
+    """Event behind the K1 forward when the backward follows in the same call (``g_known``): a consumer of log p(z)
+    on another stream waits for THIS event (``take_prior_fwd_event``), not for the whole stream."""
+    global _prior_fwd_event
+    _prior_fwd_event = torch.cuda.Event()
+    _prior_fwd_event.record(torch.cuda.current_stream())
+
+
+def take_prior_fwd_event():
+    global _prior_fwd_event
+    ev, _prior_fwd_event = _prior_fwd_event, None
+    return ev
+
+
 class _PriorLSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group, c_valid):
+    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group, c_valid, g_known=None):
         L = lib()
         z, mu, logvar = _f32(z, "z"), _f32(mu, "mu"), _f32(logvar, "logvar")
         B, D = z.shape
@@ -117,27 +134,50 @@ class _PriorLSE(torch.autograd.Function):
                                                _p(lse2), _stream()), "prior_lse_finalize")
             _count(3)
         ctx.ws_prepared = int(L.exvae_prior_lse_fwd_prepares_ws(B, C, D))
-        ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid)
         ctx.dims = (B, C, D)
+        ctx.eager = None
+        if g_known is not None and need_bwd and group is None:
+            # the upstream gradient of every row is known before the loss exists (a training step whose loss is
+            # mean(-RE + beta*KL): d loss / d log p(z_b) = -beta/B): run the backward HERE, on the forward's stream,
+            # so that it overlaps the decoder instead of sitting between the loss and the encoder backward
+            g = _f32(g_known, "g_known").reshape(-1)
+            assert g.numel() == B
+            _mark_prior_fwd_done()
+            ctx.eager = _PriorLSE._launch_bwd(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid, g, (B, C, D), ctx.ws_prepared)
+            ctx.lv_shape = logvar.shape
+            # the kernels above are only QUEUED: every buffer they read must outlive this call (a [D] logvar row made on
+            # the main stream would otherwise be freed, and reused by the decoder, before the prior branch has run)
+            ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid, g)
+            return log_p
+        ctx.save_for_backward(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid)
         return log_p
 
     @staticmethod
-    def backward(ctx, g):
+    def _launch_bwd(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid, g, dims, ws_prepared):
         L = lib()
-        z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid = ctx.saved_tensors
-        B, C, D = ctx.dims
-        g = _f32(g, "grad")
+        B, C, D = dims
         dz = torch.empty_like(z)
         dmu = torch.empty_like(mu)
         dlv = torch.empty((D,), dtype=torch.float32, device=z.device)
         L.check(L.exvae_prior_lse_bwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(lse2), _p(g),
-                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), ctx.ws_prepared, _p(c_valid), _stream()),
+                                      _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), ws_prepared, _p(c_valid), _stream()),
                 "prior_lse_bwd")
-        _count((5 if D <= 63 else 6) + (0 if ctx.ws_prepared else 1))   # D <= 63: prep, two passes, rows, dlogvar; D >= 64: W pass, two GEMMs, rows, cols, dlogvar
-        return dz, dmu, dlv.view_as(logvar), None, None, None, None, None
+        _count((5 if D <= 63 else 6) + (0 if ws_prepared else 1))   # D <= 63: prep, two passes, rows, dlogvar; D >= 64: W pass, two GEMMs, rows, cols, dlogvar
+        return dz, dmu, dlv
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.eager is not None:
+            dz, dmu, dlv = ctx.eager          # computed in forward() from the known upstream gradient
+            ctx.eager = None
+            return dz, dmu, dlv.view(ctx.lv_shape), None, None, None, None, None, None
+        z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid = ctx.saved_tensors
+        g = _f32(g, "grad")
+        dz, dmu, dlv = _PriorLSE._launch_bwd(z, mu, logvar, z_idx, mu_idx, lse2, ws, c_valid, g, ctx.dims, ctx.ws_prepared)
+        return dz, dmu, dlv.view_as(logvar), None, None, None, None, None, None
 
 
-def prior_lse(z, mu, logvar, z_idx=None, mu_idx=None, c_total=None, group=None, c_valid=None) -> torch.Tensor:
+def prior_lse(z, mu, logvar, z_idx=None, mu_idx=None, c_total=None, group=None, c_valid=None, g_known=None) -> torch.Tensor:
     """log p(z_b) = LSE_n log N(z_b | mu_n, exp(logvar)) - log(C - #masked_b)   -> [B].
 
     ``logvar`` is the [D] log-variance vector shared by all exemplars.  ``z_idx``/``mu_idx``
@@ -145,8 +185,11 @@ def prior_lse(z, mu, logvar, z_idx=None, mu_idx=None, c_total=None, group=None, 
     range-sharded bank: partial (max, sum, count) statistics are all-gathered once and merged;
     ``c_total`` is the global exemplar count.  dz/dlogvar gradients are then per-shard partials.
     ``c_valid`` ([1] int32 on the device): only the first ``c_valid`` bank rows count (fixed-capacity bank of the
-    kNN mode); the normaliser then uses that count."""
-    return _PriorLSE.apply(z, mu, logvar, z_idx, mu_idx, c_total, group, c_valid)
+    kNN mode); the normaliser then uses that count.
+    ``g_known`` ([B] on the device): the gradient of the loss w.r.t. every log p(z_b), when the caller knows it before
+    the loss is evaluated (fused training step); the backward kernels then run inside the forward call and
+    ``backward`` only hands their results out (its incoming gradient is NOT looked at)."""
+    return _PriorLSE.apply(z, mu, logvar, z_idx, mu_idx, c_total, group, c_valid, g_known)
 
 
 # ======================================================================================
@@ -426,7 +469,7 @@ class _GatedDense(torch.autograd.Function):
         fws = _ws(L.exvae_dense_fwd_workspace_bytes(R, K, O, 1), x.device)
         L.check(L.exvae_gated_dense_fwd(_p(x), _p(Wh), _p(bh), _p(Wg), _p(bg), R, K, O, _p(out), _p(s),
                                         _p(fws), fws.numel(), _stream()), "gated_dense_fwd")
-        _count(2)
+        _count(1 if Wg.data_ptr() == Wh.data_ptr() + 4 * Wh.numel() else 2)     # adjacent weights: no [Wh ; Wg] copy
         ctx.save_for_backward(x, Wh, Wg, out if need else None, s, fws if need else None)
         ctx.has_bias = (bh is not None, bg is not None)
         return out
@@ -453,6 +496,7 @@ class _GatedDense(torch.autograd.Function):
                 "gated_dense_bwd")
         _count(3 + (1 if dx is not None else 0))
         if sink is not None:
+            _keep_until_flush(ws)
             _sink_done(sink)
             return dx, None, None, None, None, None
         return dx, dWh, dbh, dWg, dbg, None
@@ -486,8 +530,39 @@ def set_grad_ready_hook(fn) -> None:
     _GRAD_READY_HOOK = fn
 
 
+_DEFER_FINISH = False
+_DEFERRED_WS = []           # workspaces a queued (deferred) dW finish still reads
+
+
+def set_deferred_dw_finish(on: bool) -> bool:
+    """When on (together with fused gradient accumulation), the backward of a LARGE dense layer queues its last pass
+    (split-K reduction of dW + bias sums into ``.grad``) on the library's side stream without joining it, so that it runs
+    next to the following layer's staging kernel; ``flush_dense_bwd()`` joins.  The caller must flush before anything
+    reads a parameter gradient (optimizer step, gradient all-reduce).  Returns the previous setting."""
+    global _DEFER_FINISH
+    prev = _DEFER_FINISH
+    if prev and not on:
+        flush_dense_bwd()
+    _DEFER_FINISH = bool(on)
+    lib().exvae_dense_bwd_defer_finish(1 if on else 0)
+    return prev
+
+
+def flush_dense_bwd() -> None:
+    """The current stream waits for every queued dW finish (no-op when none is pending)."""
+    lib().check(lib().exvae_dense_bwd_flush(_stream()), "dense_bwd_flush")
+    _DEFERRED_WS.clear()
+
+
+def _keep_until_flush(ws) -> None:
+    if _DEFER_FINISH:
+        _DEFERRED_WS.append(ws)
+
+
 def _sink_done(sink) -> None:
     if _GRAD_READY_HOOK is not None:
+        if _DEFER_FINISH:
+            flush_dense_bwd()          # the hook hands the gradient to the all-reduce: it must be complete
         for g in sink:
             if g is not None:
                 _GRAD_READY_HOOK(g, True)
@@ -547,6 +622,7 @@ class _Linear(torch.autograd.Function):
                                    1 if sink is not None else 0, _stream()), "linear_bwd")
         _count(3 + (1 if dx is not None else 0))
         if sink is not None:
+            _keep_until_flush(ws)
             _sink_done(sink)
             return dx, None, None, None, None, None, None
         return dx, dW, db, None, None, None, None
@@ -998,7 +1074,7 @@ class _PriorLSESharded(torch.autograd.Function):
     (distributed.McComm, csrc/mc_coll.cu) when the box supports it, else NCCL collectives."""
 
     @staticmethod
-    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group):
+    def forward(ctx, z, mu, logvar, z_idx, mu_idx, c_total, group, g_known=None):
         import torch.distributed as dist
         from .distributed import mc_comm
         L = lib()
@@ -1047,27 +1123,40 @@ class _PriorLSESharded(torch.autograd.Function):
         L.check(L.exvae_prior_lse_finalize(_p(all_stats), G, _p(z_all), _p(logvar), Bt, D, int(c_total), None, _p(log_p),
                                            _p(lse2), _stream()), "prior_lse_finalize")
         _count(1)
-        ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws)
         ctx.meta = (B, Bt, C, D, G, rank, group, comm, prepared)
-        return log_p[rank * B:(rank + 1) * B].clone()
+        ctx.eager = None
+        out = log_p[rank * B:(rank + 1) * B].clone()
+        if g_known is not None and any(ctx.needs_input_grad):
+            # known upstream gradient of ALL G*B rows (see prior_lse): backward + dz reduce-scatter run here, and the
+            # all-gather of the row gradients disappears
+            g_all = _f32(g_known, "g_known").reshape(-1)
+            assert g_all.numel() == Bt
+            _mark_prior_fwd_done()
+            ctx.eager = _PriorLSESharded._launch_bwd(z_all, mu, logvar, zi_all, mu_idx, lse2, ws, ctx.meta, None, g_all)
+            ctx.lv_shape = logvar.shape
+            ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws, g_all)     # keep the queued kernels' inputs alive
+        else:
+            ctx.save_for_backward(z_all, mu, logvar, zi_all, mu_idx, lse2, ws)
+        return out
 
     @staticmethod
-    def backward(ctx, g):
+    def _launch_bwd(z_all, mu, logvar, zi_all, mu_idx, lse2, ws, meta, g, g_all):
         import torch.distributed as dist
         L = lib()
-        z_all, mu, logvar, zi_all, mu_idx, lse2, ws = ctx.saved_tensors
-        B, Bt, C, D, G, rank, group, comm, prepared = ctx.meta
-        g = _f32(g, "grad")
+        B, Bt, C, D, G, rank, group, comm, prepared = meta
+        dev = z_all.device
         dmu = torch.empty_like(mu)
-        dlv = torch.empty((D,), dtype=torch.float32, device=g.device)
-        dz = torch.empty((B, D), dtype=torch.float32, device=g.device)
+        dlv = torch.empty((D,), dtype=torch.float32, device=dev)
+        dz = torch.empty((B, D), dtype=torch.float32, device=dev)
         if comm is not None:
-            g_all = comm.all_gather(g, "g").view(Bt)
+            if g_all is None:
+                g_all = comm.all_gather(g, "g").view(Bt)
             dz_all, dz_off = comm.region("dz", Bt * D)               # K1 writes its partial dz straight into the arena
             dz_all = dz_all.view(Bt, D)
         else:
-            g_all = torch.empty((Bt,), dtype=torch.float32, device=g.device)
-            dist.all_gather_into_tensor(g_all, g, group=group)
+            if g_all is None:
+                g_all = torch.empty((Bt,), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(g_all, g, group=group)
             dz_all = torch.empty_like(z_all)
         L.check(L.exvae_prior_lse_bwd(_p(z_all), _p(mu), _p(logvar), _p(zi_all), _p(mu_idx), Bt, C, D, _p(lse2),
                                       _p(g_all), _p(dz_all), _p(dmu), _p(dlv), _p(ws), ws.numel(), prepared, None, _stream()),
@@ -1078,14 +1167,25 @@ class _PriorLSESharded(torch.autograd.Function):
             _count(2)
         else:
             dist.reduce_scatter_tensor(dz, dz_all, op=dist.ReduceOp.SUM, group=group)
-        return dz, dmu, dlv.view_as(logvar), None, None, None, None
+        return dz, dmu, dlv
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.eager is not None:
+            dz, dmu, dlv = ctx.eager          # computed in forward() from the known upstream gradient
+            ctx.eager = None
+            return dz, dmu, dlv.view(ctx.lv_shape), None, None, None, None, None
+        z_all, mu, logvar, zi_all, mu_idx, lse2, ws = ctx.saved_tensors
+        dz, dmu, dlv = _PriorLSESharded._launch_bwd(z_all, mu, logvar, zi_all, mu_idx, lse2, ws, ctx.meta,
+                                                    _f32(g, "grad"), None)
+        return dz, dmu, dlv.view_as(logvar), None, None, None, None, None
 
 
-def prior_lse_sharded(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total: int, group) -> torch.Tensor:
+def prior_lse_sharded(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total: int, group, g_known=None) -> torch.Tensor:
     """``prior_lse`` for a bank range-sharded over ``group``: returns log p(z_b) for the LOCAL rows.
     Gradients: dz local (summed over shards), dmu for the local shard, dlogvar = this shard's share
     (the data-parallel gradient all-reduce completes it, like every other replicated parameter)."""
-    return _PriorLSESharded.apply(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total, group)
+    return _PriorLSESharded.apply(z, mu_shard, logvar, z_idx, mu_idx_shard, c_total, group, g_known)
 
 
 # ======================================================================================

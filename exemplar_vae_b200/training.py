@@ -1,6 +1,8 @@
 """Training loop — mirror of utils/training.py:5-51, plus a CUDA-graph captured step."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -71,6 +73,15 @@ class GraphedTrainStep:
         self.out = torch.zeros(3, dtype=torch.float32, device=dev)
         self.beta_dev = torch.full((1,), float(beta), dtype=torch.float32, device=dev)
         self._g3 = torch.tensor([1.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        # The loss of this step is mean_b(-RE_b + beta*KL_b) with KL_b = log q_b - log p(z_b), and the backward starts
+        # from d loss = 1: d loss / d log p(z_b) = -beta/B for every row (all G*B rows when the bank is range-sharded:
+        # every rank's loss has the same form).  Announcing it lets the K1 backward run right behind the K1 forward
+        # on the prior branch, overlapping the decoder, instead of between the loss and the encoder backward.
+        import os as _os
+        self.batch_size = batch_size
+        rows = batch_size * (getattr(model, "bank_world", 1) if getattr(model, "bank_group", None) is not None else 1)
+        self.g_prior = (torch.full((rows,), -float(beta) / batch_size, dtype=torch.float32, device=dev)
+                        if _os.environ.get("EXVAE_EAGER_PRIOR_BWD", "1") != "0" else None)
         self.rng_override = rng_override
         self.cache = cache
         self.graph = None
@@ -97,7 +108,13 @@ class GraphedTrainStep:
         self._restore(saved)
         if use_graph:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # Captured on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were captured on,
+            # and the prior branch (model._prior_stream(), default = low priority) runs whole-GPU K1 kernels next to the
+            # decoder's small ones.  With equal priorities the block scheduler finishes dispatching a K1 kernel's second
+            # wave before it looks at the decoder's kernels (measured: 20 us holes in the decoder backward); with the
+            # main chain at high priority its CTAs take the first SMs that come free.
+            cap = torch.cuda.Stream(priority=-1) if os.environ.get("EXVAE_GRAPH_PRIORITY", "1") != "0" else None
+            with torch.cuda.graph(self.graph, stream=cap):
                 self._body()
         torch.cuda.synchronize()
 
@@ -146,6 +163,8 @@ class GraphedTrainStep:
     def set_beta(self, beta: float):
         """New KL weight for the following steps (no re-capture: the kernels read the device scalar)."""
         self.beta_dev.fill_(float(beta))
+        if self.g_prior is not None:
+            self.g_prior.fill_(-float(beta) / self.batch_size)
 
     def _body(self):
         model = self.model
@@ -155,6 +174,8 @@ class GraphedTrainStep:
         if ro is not None:
             model.rng_override = {"eps": list(ro.get("eps", [])), "exemplar_indices": ro.get("exemplar_indices")}
         prev = ops.set_fused_grad_accumulation(True)             # dW/db are added into the flat buffer in-kernel
+        prev_defer = ops.set_deferred_dw_finish(os.environ.get("EXVAE_DEFER_DW_FINISH", "1") != "0")
+        model.prior_grad_known = self.g_prior
         try:
             loss, RE, KL = model.calculate_loss((x, self.indices), self.beta_dev, average=True, cache=self.cache,
                                                 dataset=self.dataset)
@@ -165,7 +186,10 @@ class GraphedTrainStep:
             else:
                 loss.backward()
         finally:
+            ops.flush_dense_bwd()                  # every parameter gradient is complete from here on
+            ops.set_deferred_dw_finish(prev_defer)
             ops.set_fused_grad_accumulation(prev)
+            model.prior_grad_known = None
         if model.grad_sync is not None:
             model.grad_sync()                      # data-parallel: all-reduce of the flat gradient buffer
         self.opt.step()

@@ -187,6 +187,15 @@ EXVAE_API int exvae_gemm_backend(void);
  * prior_bwd_tc.cu); NULL switches tracing off.  Keep the stamps out of hot loops: a %globaltimer read is slow. */
 EXVAE_API int exvae_gemm_set_trace(uint64_t* buf);
 
+/* Deferred finish of the weight gradients (utils/training.py:38-39: `loss.backward(); optimizer.step()` -- nothing reads
+ * a parameter gradient between the two).  With on != 0 the *_dense_bwd / linear_bwd calls of LARGE layers (R > 4096,
+ * accumulate != 0) queue their last pass (split-K reduction of dW + bias column sums, added into dW / db) on the
+ * library's side stream and return WITHOUT joining it; exvae_dense_bwd_flush(stream) makes `stream` wait for every
+ * queued finish.  The caller keeps each call's workspace alive until the flush and flushes before anything reads the
+ * gradients.  Returns the previous setting (defer_finish) / 0 (flush).  Graph-capturable (event fork / join). */
+EXVAE_API int exvae_dense_bwd_defer_finish(int on);
+EXVAE_API int exvae_dense_bwd_flush(exvae_stream_t stream);
+
 /* ---------------------------------------------------------------- convolution support (K4)
  * GatedConv2d / Conv2d (utils/nn.py:72-114) and the weight-normed conv / ELU / Upsample blocks of
  * models/fully_conv.py:12-81 run as  im2col -> dense-layer GEMM (K3, fused gate/bias/activation)
