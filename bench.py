@@ -301,7 +301,11 @@ def sharded_parity(a, args, dataset, dev, world, rank):
     D.shard_bank(m, None, dist.group.WORLD)
     sl = slice(rank * B, (rank + 1) * B)
     m.rng_override = {"eps": [e[sl].to(dev) for e in eps], "exemplar_indices": ex_idx.to(dev)}
+    # as in GraphedTrainStep (the timed path): the loss is mean(-RE + beta*KL), so d loss / d log p(z_b) = -beta/B is
+    # announced and the sharded K1 backward + dz reduce-scatter run right behind the K1 forward
+    m.prior_grad_known = torch.full((B * world,), -0.7 / B, dtype=torch.float32, device=dev)
     loss, RE, KL = m.calculate_loss((x[sl].to(dev), bidx[sl].view(-1, 1).to(dev)), 0.7, average=True, dataset=dataset)
+    m.prior_grad_known = None
     loss.backward()
     m.grad_sync()
     l3 = torch.stack((loss.detach(), RE.detach(), KL.detach()))
