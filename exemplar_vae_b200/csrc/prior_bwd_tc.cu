@@ -50,6 +50,7 @@ struct BwdP {
   int Bpad, Cpad, KP, NG, LD, B, C, D, ny, nsplit;
   float* dzs_part; float* rowsum_part; float* dmu; float* coldot_part;
   float* gcol_part; float* tot_part;
+  int x0;                      // TR: first bank tile of this launch (pass 2 goes out in single-wave chunks)
   unsigned long long* trace;   // debug (exvae_gemm_set_trace): 8 words per CTA, null in production
 };
 
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   // TR = true : X = bank tile blockIdx.x,            Y = row blocks [y0, y1) of split blockIdx.y (of gridDim.y: a
   //             range-sharded bank has few exemplar tiles per rank, so the row blocks are split over CTAs as well
   //             and prior_bwd_cols_kernel adds the partials in a fixed order)
-  const int xi = TR ? blockIdx.x : blockIdx.y;
+  const int xi = TR ? (int)blockIdx.x + p.x0 : (int)blockIdx.y;
   const int y0 = TR ? (int)(((long long)p.ny * blockIdx.y) / gridDim.y) : (int)(((long long)p.ny * blockIdx.x) / p.nsplit);
   const int y1 = TR ? (int)(((long long)p.ny * (blockIdx.y + 1)) / gridDim.y)
                     : (int)(((long long)p.ny * (blockIdx.x + 1)) / p.nsplit);
@@ -457,8 +458,18 @@ int prior_bwd_tc_launch(const PriorBwdTcArgs& a, int* nsplit_out, int* ntile_out
   p.ny = rbs; p.nsplit = 1;
   p.trace = tc_take_trace(8 * 400);
   const int rsplit = (a.gcol_part && a.tot_part) ? prior_bwd_pass2_splits(a.Bpad, a.Cpad) : 1;
-  rc = a.zip ? launch(prior_bwd_tc_kernel<true, true>, dim3(ntile, rsplit), mm, mz, mzt)
-             : launch(prior_bwd_tc_kernel<true, false>, dim3(ntile, rsplit), mm, mz, mzt);
+  // More tiles than SMs (cfg2: 196): equal single-wave chunks (2 x 98) instead of one grid of 148 + 48 CTAs.  The time is
+  // the same two waves, but no launch ever has CTAs PENDING -- the block scheduler dispatches in order, so a kernel with
+  // pending CTAs holds back every later kernel of the step (measured: 20 us holes in the decoder backward that runs next
+  // to this pass) -- and a third of the SMs stays free for those kernels.
+  const int nwave = std::max(1, ceil_div(ntile * rsplit, sm_count()));
+  const int chunk = ceil_div(ntile, nwave);
+  for (int x0 = 0; x0 < ntile && !rc; x0 += chunk) {
+    p.x0 = x0;
+    const dim3 grid(std::min(chunk, ntile - x0), rsplit);
+    rc = a.zip ? launch(prior_bwd_tc_kernel<true, true>, grid, mm, mz, mzt)
+               : launch(prior_bwd_tc_kernel<true, false>, grid, mm, mz, mzt);
+  }
   if (rc || rsplit == 1) return rc;
   const size_t sh = sizeof(float) * (128 * (a.NG + 1) + 4 * a.NG);
   prior_bwd_cols_kernel<<<ntile, 512, sh, st>>>(a.gcol_part, a.tot_part, a.ms, a.isig, rsplit, a.C, a.D, a.LD, a.NG, a.Cpad,

@@ -162,7 +162,13 @@ class _PriorLSE(torch.autograd.Function):
         L.check(L.exvae_prior_lse_bwd(_p(z), _p(mu), _p(logvar), _p(z_idx), _p(mu_idx), B, C, D, _p(lse2), _p(g),
                                       _p(dz), _p(dmu), _p(dlv), _p(ws), ws.numel(), ws_prepared, _p(c_valid), _stream()),
                 "prior_lse_bwd")
-        _count((5 if D <= 63 else 6) + (0 if ws_prepared else 1))   # D <= 63: prep, two passes, rows, dlogvar; D >= 64: W pass, two GEMMs, rows, cols, dlogvar
+        # D <= 63: prep, pass 1, pass 2 (one launch per wave of bank tiles), rows, dlogvar; D >= 64: W pass, two GEMMs, rows,
+        # cols, dlogvar
+        extra = 0
+        if D <= 63:
+            sms = torch.cuda.get_device_properties(z.device).multi_processor_count
+            extra = max(0, -(-(-(-C // 128)) // sms) - 1)
+        _count((5 if D <= 63 else 6) + extra + (0 if ws_prepared else 1))
         return dz, dmu, dlv
 
     @staticmethod

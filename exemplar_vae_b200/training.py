@@ -108,13 +108,11 @@ class GraphedTrainStep:
         self._restore(saved)
         if use_graph:
             self.graph = torch.cuda.CUDAGraph()
-            # Captured on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were captured on,
-            # and the prior branch (model._prior_stream(), default = low priority) runs whole-GPU K1 kernels next to the
-            # decoder's small ones.  With equal priorities the block scheduler finishes dispatching a K1 kernel's second
-            # wave before it looks at the decoder's kernels (measured: 20 us holes in the decoder backward); with the
-            # main chain at high priority its CTAs take the first SMs that come free.
-            cap = torch.cuda.Stream(priority=-1) if os.environ.get("EXVAE_GRAPH_PRIORITY", "1") != "0" else None
-            with torch.cuda.graph(self.graph, stream=cap):
+            # (Negative result, profiles/r2_step_schedule.md: capturing on a high-priority stream and instantiating the
+            #  graph with cudaGraphInstantiateFlagUseNodePriority changed nothing measurable; what removed the holes
+            #  next to the whole-GPU K1 kernels was to give no launch pending CTAs and to keep the small kernels' CTAs
+            #  small enough to fit next to a resident K1 CTA.)
+            with torch.cuda.graph(self.graph):
                 self._body()
         torch.cuda.synchronize()
 
