@@ -608,6 +608,20 @@ def single_conv_loss(p, args, x, x_indices, eps, exemplars, exemplar_indices, be
 
 
 # ---- deterministic synthetic parameters (large conv models: fixtures store seeds, not tensors) ----
+def grad_projections(arr, name: str, k: int = 8) -> np.ndarray:
+    """k dot products (float64) of the WHOLE flattened tensor with Rademacher (+-1) vectors seeded by the parameter name.
+    The compact conv goldens keep these instead of full gradients: every element enters every projection, so an error
+    anywhere in a tensor (a transposed filter, a swapped channel, a wrong tap order) moves them by O(||g||)."""
+    import zlib
+    a = np.asarray(arr, dtype=np.float64).reshape(-1)
+    rs = np.random.RandomState(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    out = np.empty(k, dtype=np.float64)
+    for i in range(k):
+        sgn = rs.randint(0, 2, size=a.size).astype(np.float64) * 2.0 - 1.0
+        out[i] = float(np.dot(sgn, a))
+    return out
+
+
 def synth_params(shapes: Dict[str, tuple], seed: int = 0) -> Dict[str, torch.Tensor]:
     """Reproducible parameter values keyed by state_dict name: N(0, 1/fan_in) weights, small biases,
     positive weight-norm gains.  BatchNorm tensors of the never-applied ``block.normalization``

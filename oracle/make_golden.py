@@ -207,6 +207,8 @@ def golden_model_step(model_name, hidden, seed, side=28, T=128, N=64, B=12, chan
         out = {"shape:" + k[2:]: np.asarray(v.shape, dtype=np.int64) for k, v in before.items()}
         out.update({"gh:" + k[2:]: head(v) for k, v in grads.items()})
         out.update({"gn:" + k[2:]: np.float64(np.linalg.norm(np.asarray(v, dtype=np.float64))) for k, v in grads.items()})
+        from oracle.exvae_oracle import grad_projections          # 8 seeded +-1 projections of the WHOLE gradient
+        out.update({"gp:" + k[2:]: grad_projections(v, k[2:]) for k, v in grads.items()})
         out.update({"nh:" + k[2:]: head(v) for k, v in new.items() if v.dtype == np.float32})
         out["seed"] = np.int64(seed)
     else:

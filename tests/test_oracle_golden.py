@@ -186,6 +186,9 @@ def _compact_check(g, model_name):
             gr = p[name].grad.numpy()
             _close(np.linalg.norm(gr.astype(np.float64)), g[k], rtol=2e-3)
             _close(gr.reshape(-1)[:48], g["gh:" + name], rtol=5e-3, atol=2e-3 * (np.abs(g["gh:" + name]).max() + 1e-8))
+            # every element of the tensor: seeded +-1 projections recorded from the reference's gradient
+            proj = O.grad_projections(gr, name)
+            assert np.abs(proj - g["gp:" + name]).max() <= 1e-3 * float(g[k]) + 1e-7, (name, proj, g["gp:" + name])
 
 
 def test_convhvae_training_step(golden):
