@@ -513,13 +513,21 @@ def run_gpu(a):
     tf32_peak = bf16_peak / 2.0
     ach_alg = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
     top = sorted(shapes.items(), key=lambda kv: -kv[1][0])[:8]
+    # DRAM bytes of the dominant kernel from the committed ncu capture -- only for the shape it was captured at
+    g_traffic, g_traffic_note = None, None
+    gp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(gp) and world == 1 and a.config == "cfg2" and not a.approximate:
+        gj = json.load(open(gp))
+        g_traffic = gj.get("dram_bytes_per_step_encoder_gemms")
+        g_traffic_note = ("per step = sum over the 8 encoder GEMM launches (layer-1/2/head forward, dx, dW), cfg2, 1 GPU, "
+                          "from profiles/gemm_traffic.json (ncu --set full, cold cache; per-launch figures there)")
     roofline = {
         "kernel": "gemm_tf32x3_kernel — every dense-layer / convolution C-ABI call of one step (gated_dense, linear, conv2d "
                   "fwd+bwd, incl. their staging/finish kernels): the dominant kernel of the step",
         "bound": "tensor",
         "achieved": 3.0 * ach_alg if ach_alg else None,
         "peak": tf32_peak, "unit": "TFLOP/s", "frac": (3.0 * ach_alg / tf32_peak) if ach_alg else None,
-        "traffic": None,
+        "traffic": g_traffic, "traffic_note": g_traffic_note,
         "algorithmic_tflops": ach_alg, "algorithmic_gflop_per_step": gemm_flops / 1e9, "ms_per_step": gemm_ms,
         "peak_source": f"{peak_src}: dense bf16 {bf16_peak} TFLOP/s / 2 as the TF32 estimate",
         "model": "achieved = ISSUED tf32 flops = 3 x algorithmic fp32 GEMM flops (error-compensated 3xTF32: the 1e-4 "
