@@ -109,6 +109,7 @@ class BaseModel(nn.Module, ABC):
         self._log_p_z_early = None
         self._log_q_early = None                    # log q(z|x) computed together with z in forward()
         self._side_streams = {}
+        self._exemplar_prefetch = None              # GraphedTrainStep: persistent fused operand filled one step ahead
         self._zero_rows = {}
         self._resident_cache = {}
 
@@ -444,11 +445,19 @@ class BaseModel(nn.Module, ABC):
         dev = x.device
         B = x.shape[0]
         P = int(np.prod(self.args.input_size))
-        exemplars_indices = self._exemplar_indices(dev)
-        n = exemplars_indices.numel()
-        rows = torch.empty((B + n, P), dtype=torch.float32, device=dev)
-        rows[:B].copy_(x.reshape(B, P))
-        ops.gather_rows(self.resident(dataset), exemplars_indices, out=rows[B:])
+        pf = self._exemplar_prefetch
+        if pf is not None and pf["B"] == B and pf["rows"].shape[1] == P and pf["rows"].device == dev:
+            # exemplar rows (and their indices) of THIS step were drawn and gathered behind the previous step's backward
+            # (prefetch_exemplars): only the batch rows are copied in
+            rows, exemplars_indices = pf["rows"], pf["idx"]
+            n = exemplars_indices.numel()
+            rows[:B].copy_(x.reshape(B, P))
+        else:
+            exemplars_indices = self._exemplar_indices(dev)
+            n = exemplars_indices.numel()
+            rows = torch.empty((B + n, P), dtype=torch.float32, device=dev)
+            rows[:B].copy_(x.reshape(B, P))
+            ops.gather_rows(self.resident(dataset), exemplars_indices, out=rows[B:])
         h = self._trunk(rows)
         h, h_batch = ops.shared_rows(h, B)          # mean head: all rows; log-variance head: batch rows only
         # The two heads only share their input: the small one (B rows, a few CTAs) runs on a side stream next to the
@@ -474,6 +483,21 @@ class BaseModel(nn.Module, ABC):
             from .distributed import ShardedBank
             exemplar_set = ShardedBank(exemplar_set, self.args.number_components)
         return (mean_batch, z_q_logvar), exemplar_set
+
+    def exemplar_count(self):
+        """Exemplars this rank draws per step (models/BaseModel.py:245; its share of a range-sharded bank)."""
+        from .distributed import shard_range
+        lo, hi = shard_range(self.args.number_components, self.bank_world, self.bank_rank)
+        return hi - lo
+
+    @torch.no_grad()
+    def prefetch_exemplars(self, pf, dataset):
+        """Draw the NEXT step's exemplar indices (BaseModel.py:245) and gather their rows (:247) into the persistent
+        fused operand ``pf = {"rows": [B+n, P], "idx": [n], "B": B}``.  GraphedTrainStep runs this behind the backward of
+        the current step, next to the optimizer: the 157 MB gather is HBM bound and nothing else of the step is."""
+        dev = pf["rows"].device
+        pf["idx"].copy_(self._exemplar_indices(dev))
+        ops.gather_rows(self.resident(dataset), pf["idx"], out=pf["rows"][pf["B"]:])
 
     def cache_z(self, dataset, prior=True, cuda=True):
         """models/BaseModel.py:223-241 — embed the whole (resident) dataset in chunks of 10 000."""

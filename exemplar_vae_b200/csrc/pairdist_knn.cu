@@ -261,19 +261,39 @@ __global__ void __launch_bounds__(1024) unique_positions_kernel(const int64_t* _
 }
 
 // ------------------------------------------------------------------------------ row movement
+// Grid = 4 CTAs per SM, all resident at once: a launch with PENDING CTAs holds back every later kernel of the step (the
+// block scheduler dispatches in order), and this gather runs next to the optimizer kernels.  Four independent 16-byte
+// loads per thread and iteration keep ~10 MB in flight, enough for the HBM latency-bandwidth product.
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                                           long long n_rows, int row_len, int vec,
                                                           float* __restrict__ out) {
   const long long per_row = row_len / vec;
   const long long total = n_rows * per_row;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const long long r = e / per_row, v = e - r * per_row;
-    const long long s = idx[r];
-    if (vec == 4)
-      reinterpret_cast<float4*>(out)[e] = reinterpret_cast<const float4*>(src + s * row_len)[v];
-    else
-      out[e] = src[s * row_len + v];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (vec == 4) {
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for (; e + 3 * stride < total; e += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long ee = e + u * stride;
+        const long long r = ee / per_row, c = ee - r * per_row;
+        v[u] = src4[idx[r] * per_row + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) out4[e + u * stride] = v[u];
+    }
+    for (; e < total; e += stride) {
+      const long long r = e / per_row, c = e - r * per_row;
+      out4[e] = src4[idx[r] * per_row + c];
+    }
+  } else {
+    for (; e < total; e += stride) {
+      const long long r = e / per_row, c = e - r * per_row;
+      out[e] = src[idx[r] * row_len + c];
+    }
   }
 }
 __global__ void __launch_bounds__(256) scatter_rows_kernel(float* __restrict__ dst, const int64_t* __restrict__ idx,
@@ -356,7 +376,7 @@ extern "C" int exvae_gather_rows(const float* src, const int64_t* idx, int n_row
   EXVAE_CHECK_ARG(src && idx && out && n_rows > 0 && row_len > 0);
   const int vec = (row_len % 4 == 0 && aligned16(src) && aligned16(out)) ? 4 : 1;
   const long long total = (long long)n_rows * (row_len / vec);
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 4);
   gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, idx, n_rows, row_len, vec, out);
   EXVAE_RETURN_LAST_ERROR();
 }

@@ -77,24 +77,36 @@ class GraphedTrainStep:
         # from d loss = 1: d loss / d log p(z_b) = -beta/B for every row (all G*B rows when the bank is range-sharded:
         # every rank's loss has the same form).  Announcing it lets the K1 backward run right behind the K1 forward
         # on the prior branch, overlapping the decoder, instead of between the loss and the encoder backward.
-        import os as _os
         self.batch_size = batch_size
         rows = batch_size * (getattr(model, "bank_world", 1) if getattr(model, "bank_group", None) is not None else 1)
         self.g_prior = (torch.full((rows,), -float(beta) / batch_size, dtype=torch.float32, device=dev)
-                        if _os.environ.get("EXVAE_EAGER_PRIOR_BWD", "1") != "0" else None)
+                        if os.environ.get("EXVAE_EAGER_PRIOR_BWD", "1") != "0" else None)
         self.rng_override = rng_override
         self.cache = cache
+        # Exemplar prefetch: the next step's N exemplar indices are drawn, and their rows gathered into a persistent
+        # [B+N, P] operand, behind the backward of the current step (next to the optimizer), so the step does not start
+        # with a 27 us HBM-bound gather in front of the first GEMM.  Every step still draws and encodes a fresh exemplar
+        # set.  With injected indices (tests) the tensor must hold the NEXT step's indices when a step runs;
+        # ``prime_exemplars()`` (re)loads the first set.
+        self.prefetch = (os.environ.get("EXVAE_PREFETCH_EXEMPLARS", "1") != "0" and dataset is not None
+                         and getattr(args, "prior", None) == "exemplar_prior" and args.approximate_prior is False
+                         and getattr(model, "fuse_exemplar_encoder", False))
+        self._pf = None
+        if self.prefetch:
+            n = model.exemplar_count()
+            self._pf = {"rows": torch.zeros(batch_size + n, P, dtype=torch.float32, device=dev),
+                        "idx": torch.zeros(n, dtype=torch.int64, device=dev), "B": batch_size}
         self.graph = None
         self.launches_per_step = 0
         if getattr(model, "flat_grads", None) is None:
             from .distributed import FlatGrads
             model.flat_grads = FlatGrads(model.parameters())     # stable grad pointers, one memset per step
-        import os
         # prior || decoder as parallel graph branches (EXVAE_OVERLAP_SHARDED=0: only with a replicated bank)
         model.overlap_prior = (getattr(model, "bank_group", None) is None
                                or os.environ.get("EXVAE_OVERLAP_SHARDED", "1") != "0")
         model.train()
         saved = self._snapshot()
+        self.prime_exemplars()
         # eager warm-up on a side stream (allocator + optimizer state + grad buffers settle)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -106,6 +118,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore(saved)
+        self.prime_exemplars()            # from the restored RNG state: the first real step's exemplar set
         if use_graph:
             self.graph = torch.cuda.CUDAGraph()
             # (Negative result, profiles/r2_step_schedule.md: capturing on a high-priority stream and instantiating the
@@ -158,6 +171,16 @@ class GraphedTrainStep:
         self.model.flat_grads.zero_()
         self.out.zero_()
 
+    def prime_exemplars(self):
+        """Draw + gather the exemplar set of the NEXT step now (no-op without prefetch).  Called by the constructor; call
+        it again after changing injected indices (``rng_override``) or the RNG state by hand."""
+        if self.prefetch:
+            ro, model = self.rng_override, self.model
+            if ro is not None:
+                model.rng_override = {"eps": list(ro.get("eps", [])), "exemplar_indices": ro.get("exemplar_indices")}
+            model.prefetch_exemplars(self._pf, self.dataset)
+            torch.cuda.current_stream().synchronize()
+
     def set_beta(self, beta: float):
         """New KL weight for the following steps (no re-capture: the kernels read the device scalar)."""
         self.beta_dev.fill_(float(beta))
@@ -174,6 +197,8 @@ class GraphedTrainStep:
         prev = ops.set_fused_grad_accumulation(True)             # dW/db are added into the flat buffer in-kernel
         prev_defer = ops.set_deferred_dw_finish(os.environ.get("EXVAE_DEFER_DW_FINISH", "1") != "0")
         model.prior_grad_known = self.g_prior
+        model._exemplar_prefetch = self._pf
+        aux = None
         try:
             loss, RE, KL = model.calculate_loss((x, self.indices), self.beta_dev, average=True, cache=self.cache,
                                                 dataset=self.dataset)
@@ -183,11 +208,21 @@ class GraphedTrainStep:
                 torch.autograd.backward(base, grad_tensors=self._g3)
             else:
                 loss.backward()
+            if self.prefetch:
+                # the backward has consumed the fused operand (its last reader, the layer-1 dW GEMM, is on this stream;
+                # the deferred dW finishes read only their own workspaces): fill it for the next step on a side
+                # branch, next to the gradient exchange / optimizer below (joined at the end of the step)
+                cur = torch.cuda.current_stream()
+                aux = model._aux_stream()
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    model.prefetch_exemplars(self._pf, self.dataset)
         finally:
             ops.flush_dense_bwd()                  # every parameter gradient is complete from here on
             ops.set_deferred_dw_finish(prev_defer)
             ops.set_fused_grad_accumulation(prev)
             model.prior_grad_known = None
+            model._exemplar_prefetch = None
         if model.grad_sync is not None:
             model.grad_sync()                      # data-parallel: all-reduce of the flat gradient buffer
         self.opt.step()
@@ -197,6 +232,8 @@ class GraphedTrainStep:
                 self.out.copy_(base.detach())
             else:
                 self.out.copy_(torch.stack((loss.detach(), RE.detach(), KL.detach())))
+        if aux is not None:
+            torch.cuda.current_stream().wait_stream(aux)
 
     def step(self, data=None, indices=None):
         if data is not None:

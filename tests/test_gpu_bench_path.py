@@ -104,10 +104,16 @@ def test_graphed_step_matches_eager_and_oracle_at_baseline_size(model_name, B, N
     assert int(opt_g._tables[0]["step"].item()) == 0
     step.set_beta(beta)                          # device scalar: no re-capture
     graph_losses = []
-    for bidx, x, ex_idx, eps in draws:
+    # exemplar prefetch: a step gathers the NEXT step's exemplar rows behind its backward, so the injected index tensor
+    # holds step k+1's draw while step k runs; prime_exemplars() loads the first set
+    assert step.prefetch
+    static["exemplar_indices"].copy_(draws[0][2])
+    step.prime_exemplars()
+    for k, (bidx, x, ex_idx, eps) in enumerate(draws):
         for dst, e in zip(static["eps"], eps):
             dst.copy_(e)
-        static["exemplar_indices"].copy_(ex_idx)
+        if k + 1 < len(draws):
+            static["exemplar_indices"].copy_(draws[k + 1][2])
         out = step.step(x.cuda(), bidx.cuda())
         graph_losses.append(tuple(out.tolist()))
     assert int(opt_g._tables[0]["step"].item()) == steps
