@@ -423,6 +423,30 @@ __global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict_
                                                         int accumulate) {
   if ((int)blockIdx.x < nred) {
     const size_t total = (size_t)M * N;
+    // 16-byte path (N % 4 == 0 and aligned planes / destinations: a float4 never straddles a row or the out0 | out1
+    // boundary): a quarter of the threads and instructions of the scalar loop -- this pass is launch / latency bound and,
+    // for the first layer, sits between the last GEMM of the backward and the optimizer
+    const bool v4 = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out0) |
+                                      reinterpret_cast<uintptr_t>(out1)) & 15) == 0;
+    if (v4) {
+      const size_t total4 = total >> 2;
+      for (size_t e4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e4 < total4; e4 += (size_t)nred * blockDim.x) {
+        const size_t e = e4 << 2;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < S; ++s) {
+          const float4 t = *reinterpret_cast<const float4*>(part + (size_t)s * total + e);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        const int m = (int)(e / N);
+        float4* dst = reinterpret_cast<float4*>(m < mseg ? out0 + e : out1 + (e - (size_t)mseg * N));
+        if (accumulate) {
+          const float4 o = *dst;
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+        }
+        *dst = a;
+      }
+      return;
+    }
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)nred * blockDim.x) {
       float a = 0.f;
       for (int s = 0; s < S; ++s) a += part[(size_t)s * total + e];
@@ -670,7 +694,9 @@ int dense_bwd_tc(const float* x, const float* W0, const float* W1, int R, int K,
       sw = dside->stream;
       dside->pending = true;
     }
-    const int nred = ew_blocks((long long)ncat * K);
+    // (same test as the kernel's 16-byte path: then a quarter of the blocks)
+    const bool v4 = (K & 3) == 0 && al16(part) && al16(dW0) && al16(dW1 ? dW1 : dW0);
+    const int nred = ew_blocks((long long)ncat * K / (v4 ? 4 : 1));
     const int ncs = (db0 || db1) ? ceil_div(ncat, 32) : 0;
     dw_finish_kernel<<<nred + ncs, 256, 0, sw>>>(part, plan.S, ncat, K, oseg, dW0, dW1 ? dW1 : dW0, nred,
                                                  reinterpret_cast<const float*>(ws + plan.off_cs), plan.S2, ncat, db0,

@@ -10,3 +10,5 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tf32x3|prior_|knn_fused' -c 48 -f -o gpurun_out/${tag}_prof python tools/prof_kernels.py > gpurun_out/${tag}_prof.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out/${tag}_prof.ncu-rep
+timeout 300 python tools/timeline.py > gpurun_out/${tag}_timeline_cfg2.md 2> gpurun_out/${tag}_timeline.err; echo "timeline rc=$?"
+timeout 300 python bench.py --config cfg4 --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_bench_cfg4.json 2> gpurun_out/${tag}_bench_cfg4.err; echo "bench4 rc=$?"
