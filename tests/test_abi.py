@@ -4,6 +4,8 @@ mirror keeps the reference's state_dict keys."""
 import ctypes
 import os
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -152,3 +154,43 @@ def test_vampprior_state_dict_keys_match_the_reference(golden):
     got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     assert got == want
     assert "prior_log_variance" not in got and got["means.linear.weight"] == (side * side, len(g["ex_idx"]))
+
+
+def test_gated_dense_keeps_its_two_weights_adjacent():
+    """layers.GatedDense stores h.weight / g.weight in one [2*O, K] buffer (the GEMM reads [Wh ; Wg] as one operand, no
+    concat launch); names, shapes, state_dict and load_state_dict are the reference's (utils/nn.py:44-69), and a module
+    that lost the adjacency (deepcopy) is still a valid module (the C side copies then)."""
+    import copy
+    from exemplar_vae_b200.layers import GatedDense
+    m = GatedDense(784, 300)
+    adj = lambda mod: mod.g.weight.data_ptr() == mod.h.weight.data_ptr() + mod.h.weight.numel() * 4
+    assert adj(m) and m.h.weight.is_contiguous() and m.g.weight.is_contiguous()
+    assert list(m.state_dict().keys()) == ["h.weight", "h.bias", "g.weight", "g.bias"]
+    sd = {k: torch.randn_like(v) for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    assert adj(m) and torch.equal(m.h.weight, sd["h.weight"]) and torch.equal(m.g.weight, sd["g.weight"])
+    m2 = m.double().float()                      # Module._apply moves every parameter on its own: re-packed afterwards
+    assert adj(m2) and torch.equal(m2.g.weight, sd["g.weight"])
+    m3 = copy.deepcopy(m)
+    assert torch.equal(m3.h.weight, m.h.weight) and torch.equal(m3.g.weight, m.g.weight)
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    (m.h.weight.sum() + 2 * m.g.weight.sum()).backward()
+    opt.step()                                   # in-place updates through the two views hit the shared buffer
+    assert torch.allclose(m.h.weight, sd["h.weight"] - 0.5) and torch.allclose(m.g.weight, sd["g.weight"] - 1.0) and adj(m)
+
+
+def test_grad_projections_see_every_element_and_orderings():
+    """oracle.grad_projections (the whole-tensor check of the compact conv goldens): deterministic per name, linear,
+    and a transposed filter / swapped channel moves it by O(||g||)."""
+    from oracle import exvae_oracle as O
+    rs = np.random.RandomState(0)
+    g = rs.randn(64, 32, 3, 3)
+    p = O.grad_projections(g, "q_z_layers.0.h.weight")
+    assert np.array_equal(p, O.grad_projections(g.copy(), "q_z_layers.0.h.weight"))
+    assert not np.allclose(p, O.grad_projections(g, "q_z_layers.0.g.weight"))
+    assert np.allclose(O.grad_projections(2 * g, "q_z_layers.0.h.weight"), 2 * p)
+    nrm = np.linalg.norm(g)
+    for wrong in (g.transpose(0, 1, 3, 2), g[:, ::-1], g[::-1]):
+        assert np.abs(O.grad_projections(np.ascontiguousarray(wrong), "q_z_layers.0.h.weight") - p).max() > 0.05 * nrm
+    e = np.zeros_like(g); e[63, 31, 2, 2] = 1.0             # the very last element enters every projection
+    assert np.all(np.abs(O.grad_projections(e, "x")) == 1.0)
