@@ -202,6 +202,37 @@ __global__ void __launch_bounds__(256) up2_bwd_kernel(const float* __restrict__ 
 
 }  // namespace
 
+
+namespace {
+// one thread per 16-byte group of the padded frame
+__global__ void __launch_bounds__(256) pad_frame_kernel(const float4* __restrict__ src, int N, int h, int w, int C4, int Hp,
+                                                        int Wp, int oy0, int ox0, float4* __restrict__ dst) {
+  const unsigned long long total = (unsigned long long)N * Hp * Wp * C4;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned c = (unsigned)(e % C4);
+    const unsigned long long pix = e / C4;
+    const unsigned x = (unsigned)(pix % Wp);
+    const unsigned long long t = pix / Wp;
+    const unsigned y = (unsigned)(t % Hp), n = (unsigned)(t / Hp);
+    const int sy = (int)y - oy0, sx = (int)x - ox0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sy >= 0 && sy < h && sx >= 0 && sx < w) v = src[(((size_t)n * h + sy) * w + sx) * C4 + c];
+    dst[e] = v;
+  }
+}
+}  // namespace
+
+int conv_pad_frame(const float* src, int N, int h, int w, int C, int Hp, int Wp, int oy0, int ox0, float* dst,
+                   cudaStream_t st) {
+  if ((C & 3) || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return EXVAE_ERR_INVALID_ARG;
+  const long long total = (long long)N * Hp * Wp * (C / 4);
+  pad_frame_kernel<<<ew_blocks(total), 256, 0, st>>>(reinterpret_cast<const float4*>(src), N, h, w, C / 4, Hp, Wp, oy0, ox0,
+                                                     reinterpret_cast<float4*>(dst));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EXVAE_OK : (int)e;
+}
+
 int conv_im2col(const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int OH, int OW, int ldk,
                 float* col, cudaStream_t st) {
   const bool v4 = C % 4 == 0 && ldk % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&

@@ -1024,10 +1024,42 @@ extern "C" int exvae_conv2d_bwd(const float* x, const float* wbw, const float* o
     EXVAE_CUDA(cudaGetLastError());
   }
   int rc;
-  // 2. weight gradient: patches recomputed (never saved by the forward), dWcat = dcat^T . col, split over the pixels
-  rc = conv_im2col(x, N, H, W, Cin, KH, KW, stride, pad, c.OH, c.OW, c.Kpc, col, st);
-  if (rc) return rc;
-  {
+  // 2. weight gradient.
+  // Stride 1 and Cin % 32 == 0: IMPLICIT.  Both operands are copied into one zero-padded frame [N][Hp][Wp] (Hp = H + 2 pad,
+  // output pixel (oy, ox) at frame position (oy, ox), input pixel (iy, ix) at (iy + pad, ix + pad)); then the input pixel of
+  // tap (ky, kx) sits at the CONSTANT row offset ky*Wp + kx from the output pixel, every out-of-image read lands in the
+  // zero border, and dW[co][tap][ci] = sum_q dYp[q][co] * Xp[q + ky*Wp + kx][ci] is a plain split-K GEMM whose B tile is
+  // loaded with a per-tap row shift (TcGemm::dwc_*).  No patch matrix: 2 x 1.15 x (in + dcat) of copies instead of
+  // 2 x taps x in.
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const long long Q = (long long)N * Hp * Wp;
+  static const bool dw_implicit_on = [] { const char* e = getenv("EXVAE_CONV_DW_IMPLICIT"); return !(e && strcmp(e, "0") == 0); }();
+  const bool dw_implicit = dw_implicit_on && stride == 1 && Cin % 32 == 0 && c.Kpc == c.taps * Cin && Q < (1ll << 31) &&
+                           c.OH == Hp - KH + 1 && c.OW == Wp - KW + 1 &&
+                           (size_t)Q * (c.ldd + Cin) <= (size_t)R * c.Kpc;      // the frames fit into the patch region
+  if (dw_implicit) {
+    float* dyp = col;                                   // [Q][ldd]
+    float* xp = col + (size_t)Q * c.ldd;                // [Q][Cin]   (Q * ldd * 4 bytes is a multiple of 16)
+    rc = conv_pad_frame(dcat, N, c.OH, c.OW, c.ldd, Hp, Wp, 0, 0, dyp, st);
+    if (rc) return rc;
+    rc = conv_pad_frame(x, N, H, W, Cin, Hp, Wp, pad, pad, xp, st);
+    if (rc) return rc;
+    const int kchunk = ceil_div(ceil_div((int)Q, wl.gp.S), 32) * 32;
+    const int S = ceil_div((int)Q, kchunk);             // <= the planned split count: the partial planes fit
+    TcGemm g{};
+    g.a = dyp; g.a_rows = (int)Q; g.a_cols = c.ldd; g.a_mn = true;
+    g.b = xp; g.b_rows = (int)Q; g.b_cols = Cin; g.b_mn = true;
+    g.M = ncat; g.N = c.Kpc; g.K = (int)Q; g.epi = TC_SPLITK; g.out0 = part; g.ldc = c.Kpc;
+    g.splits = S; g.kchunk = kchunk;
+    g.dwc_cin = Cin; g.dwc_kw = KW; g.dwc_wp = Wp;
+    rc = tc_gemm_launch(g, st);
+    if (rc) return rc;
+    rc = conv_unpack_wgrad(part, S, ncat, c.Kpc, Cin, O, Cin, KH, KW, dW0, dW1, cs, wl.gp.S2, db0, db1, accumulate, st);
+    if (rc) return rc;
+  } else {
+    // patches recomputed (never saved by the forward), dWcat = dcat^T . col, split over the pixels
+    rc = conv_im2col(x, N, H, W, Cin, KH, KW, stride, pad, c.OH, c.OW, c.Kpc, col, st);
+    if (rc) return rc;
     TcGemm g{};
     g.a = dcat; g.a_rows = R; g.a_cols = c.ldd; g.a_mn = true;
     g.b = col; g.b_rows = R; g.b_cols = c.Kpc; g.b_mn = true;

@@ -63,6 +63,7 @@ struct TcParams {
   TcPriorEpi prior;            // TC_LSE / TC_PW epilogues
   // implicit-GEMM convolution (CONV): tile = bn images x bh output rows x OW pixels
   int cv_OH, cv_OW, cv_KW, cv_stride, cv_pad, cv_bh, cv_bn, cv_kbpt, cv_tpi, cv_mrows;
+  int dwc_cin, dwc_kw, dwc_wp;   // implicit conv weight gradient (TcGemm): tap-shifted rows of the MN-major B operand
   unsigned long long* trace;   // debug: per-CTA {start, end, tiles, SM} (tools/gemm_trace.py), null in production
 };
 unsigned long long* g_trace = nullptr;
@@ -264,8 +265,18 @@ __global__ void __launch_bounds__(TTHREADS, 1)
           } else {
             const int nch = (c.neff + 31) / 32;
 #pragma unroll
-            for (int q = 0; q < BN / 32; ++q)                                  // box {32 n, 32 k}
-              if (q < nch) tma_load_2d(sb + q * 4096, &tmB, &full[s], c.n0 + 32 * q, k0);
+            for (int q = 0; q < BN / 32; ++q) {                                // box {32 n, 32 k}
+              if (q < nch) {
+                int nn = c.n0 + 32 * q, kk = k0;
+                if (p.dwc_cin > 0) {          // column = (tap, channel): rows shifted by the tap inside the padded frame
+                  const int tap = nn / p.dwc_cin;
+                  nn -= tap * p.dwc_cin;
+                  const int ky = tap / p.dwc_kw;
+                  kk += ky * p.dwc_wp + (tap - ky * p.dwc_kw);
+                }
+                tma_load_2d(sb + q * 4096, &tmB, &full[s], nn, kk);
+              }
+            }
           }
         }
       }
@@ -734,6 +745,7 @@ static int tc_gemm_launch_bn(const TcGemm& g, cudaStream_t st) {
     p.cv_bh = cv.bh; p.cv_bn = cv.bn; p.cv_kbpt = ceil_div(cv.C, 32); p.cv_tpi = cv.OH / cv.bh;
     p.cv_mrows = cv.bn * cv.bh * cv.OW;
   }
+  p.dwc_cin = g.dwc_cin; p.dwc_kw = g.dwc_kw; p.dwc_wp = g.dwc_wp;
   p.trace = g_trace;
   if (g_trace) g_trace += 8 * 160;   // the next traced launch writes the next segment
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

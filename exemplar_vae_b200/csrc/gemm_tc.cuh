@@ -52,6 +52,10 @@ struct TcGemm {
   int splits, kchunk;  // TC_SPLITK: grid.z = splits, out0 = partial [splits][M][N]
   TcPriorEpi prior;    // TC_LSE / TC_PW
   const TcConv* conv;  // non-null: A is the implicit patch matrix of this convolution (a, a_rows, a_cols unused; a_mn = false)
+  // Implicit weight gradient of a stride-1 convolution (b_mn, dwc_cin > 0): B is the zero-padded NHWC input viewed as
+  // [pixels][dwc_cin]; output column n = tap*dwc_cin + ci reads B rows SHIFTED by the tap, k + (tap / dwc_kw) * dwc_wp +
+  // tap % dwc_kw (dwc_wp = padded image width), so no patch matrix exists.  dwc_cin % 32 == 0; b_cols == dwc_cin.
+  int dwc_cin, dwc_kw, dwc_wp;
 };
 
 bool tc_enabled();                       // sm_100 device, driver entry point found, not disabled by EXVAE_GEMM=simt
