@@ -35,6 +35,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
+    extra = os.environ.get("NVCC_EXTRA", "").split()       # e.g. -DEXVAE_PF_TRACE (debug trace of the fused K1 forward)
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "gemm_tc.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "prior_lse_tc.cuh"),
                os.path.join(CSRC, "..", "..", "include", "exvae_b200.h")]
     objs, jobs = [], []
@@ -43,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,5 +1,9 @@
 """Per-CTA phase / wait trace of the fused exemplar-prior forward kernel (prior_fused.cu); run on a B200.
 
+The trace stores are compiled in only with -DEXVAE_PF_TRACE (production builds carry no trace code: a %globaltimer
+store guarded by a kernel-parameter null check faulted under the kNN-mode test, profiles/r2_step_schedule.md):
+    NVCC_EXTRA=-DEXVAE_PF_TRACE python tools/build_lib.py --force && python tools/prior_fwd_trace.py
+
 words per CTA: 0 start, 1 prologue done, 2 converter cycles waiting for a free stage, 3 MMA cycles waiting for a converted
 stage, 4 MMA cycles waiting for a drained accumulator, 5 epilogue cycles waiting for an accumulator, 6 main loop done,
 7 end (top bit: the CTA that merged its row block)."""
