@@ -936,7 +936,15 @@ extern "C" size_t exvae_prior_lse_fwd_workspace_bytes(int B, int C, int D) {
   return std::max(prior_ws_layout(B, C, D, false, nullptr).bytes, prior_fused_ok(D) ? prior_fused_ws_bytes(B, C) : (size_t)0);
 }
 
-static inline bool fused_fwd_path(int B, int D) { return prior_fused_ok(D) && ceil_div(B, 128) <= 64; }
+// The one-kernel forward converts every bank tile once PER ROW BLOCK (its converter warps bound it at ~2.9 us per
+// 128x128 tile, profiles/r2_prior_fwd_trace.log); the staged path converts the bank once (14 us per 25 000 rows) and its
+// TMA-fed main kernel needs ~1.2 us per tile.  Measured (tools/prior_time.py): cfg2 (4 row blocks x 196 tiles, 5 tiles
+// per CTA) fused 34 us vs staged 45-55 us; the IWAE shape 5000 x 50 000 (40 x 391, 105 tiles per CTA) fused 291-414 us
+// vs staged 155-250 us.  So: one kernel up to ~12 tiles per CTA, staged operands beyond.
+static inline bool fused_fwd_path(int B, int C, int D) {
+  const long long units = (long long)ceil_div(B, 128) * ceil_div(C, 128);
+  return prior_fused_ok(D) && ceil_div(B, 128) <= 64 && units <= 12ll * sm_count();
+}
 
 extern "C" int exvae_prior_lse_fwd_prepares_ws(int B, int C, int D) {
   (void)B; (void)C; (void)D;
@@ -951,7 +959,7 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
   EXVAE_CHECK_ARG(B > 0 && C > 0 && D > 0);
   EXVAE_CHECK_ARG((log_p == nullptr) == (lse2 == nullptr));
   cudaStream_t st = as_stream(stream);
-  if (fused_fwd_path(B, D)) {
+  if (fused_fwd_path(B, C, D)) {
     // ONE kernel from the raw inputs: distance, log-density, mask, log-sum-exp, normaliser (prior_fused.cu)
     // workspace: [staged operands for the backward (only when the caller passed the fwd+bwd size)][tickets + partials]
     const size_t fb = prior_fused_ws_bytes(B, C);
@@ -1017,7 +1025,8 @@ extern "C" int exvae_prior_lse_fwd(const float* z, const float* mu, const float*
     if (rc) return rc;
     lse_merge_kernel<false><<<ceil_div(B, 8), 256, 0, st>>>(w.part, nsplit_tc, (size_t)nsplit_tc * 4, 4, B, nullptr,
                                                             nullptr, D, 0.f, stats, nullptr, nullptr);
-    EXVAE_RETURN_LAST_ERROR();
+    EXVAE_CUDA(cudaGetLastError());
+    return fin(stats);          // one-GPU callers asked for log p(z) itself (this return used to skip the final merge)
   }
   const FwdSmem L = fwd_smem_layout(w.LD);
   dim3 grid(w.nsplit, w.Bpad / PR_BM);
@@ -1058,7 +1067,7 @@ extern "C" int exvae_prior_lse_bwd(const float* z, const float* mu, const float*
   if (ws_bytes < w.bytes) return EXVAE_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   // (the one-kernel forward only leaves what the tensor-core backward reads: the FMA-pipe variant re-stages)
-  if (!ws_prepared || (fused_fwd_path(B, D) && (!w.NG || bwd_simt_forced()))) {
+  if (!ws_prepared || (fused_fwd_path(B, C, D) && (!w.NG || bwd_simt_forced()))) {
     int rc = stage(w, z, mu, logvar, mu_idx, B, C, D, c_valid, st);
     if (rc) return rc;
   }
