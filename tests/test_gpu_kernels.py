@@ -182,13 +182,15 @@ def test_prior_lse_backward_vs_oracle_cfg1(ops):
                                           (300, 1438, 40, True), (70, 900, 128, True), (5, 3, 8, False),
                                           (4096, 3125, 40, True), (1000, 2900, 40, False),
                                           (512, 12500, 128, True), (300, 3000, 64, False), (100, 700, 512, True),
-                                          (1024, 6250, 128, True)])
+                                          (1024, 6250, 128, True), (2048, 14500, 40, True)])
 def test_prior_lse_backward_vs_fp64_sizes(ops, B, C, D, masked):
     """K1 backward (tensor-core path for D <= 63, FMA-pipe path above) against fp64 torch autograd of the
     reference formula, incl. the cfg2 and cfg4-shard sizes, ragged tiles and the leave-one-out mask; the last two
     shapes are the 8-GPU shard geometry (all-gathered 8 x 512 rows against 25 000 / 8 exemplars), where pass 2 of
     the backward splits the row blocks over CTAs.  D >= 64 (cfg5's D=128 bank shard 512 x 12 500, the single_conv
-    latent D=512) runs through the persistent tcgen05 GEMM kernel with the LSE / weight epilogues."""
+    latent D=512) runs through the persistent tcgen05 GEMM kernel with the LSE / weight epilogues.  The last shape
+    (16 row blocks x 114 bank tiles > 12 tiles per CTA) takes the STAGED forward (prior_lse.cu:fused_fwd_path) followed
+    by the tensor-core backward on the operands it staged."""
     g = torch.Generator().manual_seed(B + C + D)
     mu = torch.randn(C, D, generator=g)
     lv = torch.full((D,), -2.4189) + 0.1 * torch.randn(D, generator=g)
