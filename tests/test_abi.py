@@ -46,6 +46,10 @@ def test_argument_errors_without_gpu(L):
     # fused K2: per-split candidate lists only, the [B,N] distance matrix never reaches HBM
     assert 0 < L.exvae_knn_workspace_bytes(100, 25000, 40, 10) < 100 * 25000 * 4
     assert L.exvae_gated_dense_bwd_workspace_bytes(25000, 784, 300) > 25000 * 600 * 4
+    # the deferred-finish switch is plain host state: returns the previous setting; a flush with nothing queued is a no-op
+    assert L.exvae_dense_bwd_defer_finish(1) == 0
+    assert L.exvae_dense_bwd_defer_finish(0) == 1
+    assert L.exvae_dense_bwd_flush(None) == 0
 
 
 def test_header_cites_reference_for_each_group():
